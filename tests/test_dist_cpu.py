@@ -1,0 +1,93 @@
+"""world_size-2 gloo test of the data-parallel host logic: rank r takes
+rows [r*N/G, (r+1)*N/G) of each minibatch with the loss gradient scaled by 1/N_global; the
+sum-allreduce of {gradWeight, gradSum, gradBias} equals the single-rank full-batch accumulators,
+so the replicated update is identical on every rank."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _make(opt_over=None):
+    from oracle import vbnn_oracle as O
+    opt = O.default_opt(input_size=10, hidden=[8], classes=list("abc"), S=2, B=20.0, batchSize=8,
+                        mu_init=1, var_init=0.01)
+    opt.update(opt_over or {})
+    net = O.MLPOracle(opt, torch.float64, seed=3)
+    return O, opt, net
+
+
+def _grads(O, net, opt, X, T, eps, scale_rows):
+    """accumulators after S x (sample, run) on the row shard X with dLoss scaled to the global batch"""
+    net.resetGradients()
+    for s in range(opt["S"]):
+        net.sample(eps[s])
+        x = X
+        acts = [x]
+        for lyr in net.vb:
+            acts.append(torch.clamp(lyr.updateOutput(acts[-1]), min=0))
+        logp = O.log_softmax(net.out.updateOutput(acts[-1]))
+        g = O.log_softmax_backward(logp, O.class_nll_backward(logp, T)) * scale_rows
+        g_in = net.out.updateGradInput(acts[-1], g)
+        net.out.accGradParameters(acts[-1], g, 1.0)
+        for k in range(len(net.vb) - 1, -1, -1):
+            g = g_in * (acts[k + 1] > 0).to(torch.float64)
+            g_in = net.vb[k].updateGradInput(acts[k], g)
+            net.vb[k].accGradParameters(acts[k], g, 1.0)
+    flat = []
+    for lyr in net.vb:
+        flat += [lyr.gradWeight.reshape(-1), lyr.gradSum.reshape(-1), lyr.gradBias.reshape(-1)]
+    flat += [net.out.gradWeight.reshape(-1), net.out.gradBias.reshape(-1)]
+    return torch.cat(flat)
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    O, opt, net = _make()
+    rng = np.random.RandomState(0)
+    N = 8
+    X = torch.from_numpy(rng.randn(N, 10))
+    T = torch.from_numpy(rng.randint(1, 4, N).astype(np.float64))
+    eps = [[torch.from_numpy(rng.randn(l.O, l.I)) for l in net.vb] for _ in range(opt["S"])]
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    # local criterion averages over N/world rows; rescale to the global mean (1/N_global)
+    local = _grads(O, net, opt, X[lo:hi], T[lo:hi], eps, scale_rows=(hi - lo) / N)
+    dist.all_reduce(local, op=dist.ReduceOp.SUM)
+    full = _grads(O, net, opt, X, T, eps, scale_rows=1.0)
+    ret[rank] = float((local - full).abs().max() / full.abs().max())
+    dist.destroy_process_group()
+
+
+def test_row_sharded_allreduce_equals_full_batch():
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert ret[r] < 1e-12, ret[r]
+
+
+def test_philox_rows_are_shard_invariant():
+    from oracle import vbnn_oracle as O
+    full = O.philox_normal_matrix(5, 3, 1 << 16, 0, rows=16, cols=12)
+    parts = [O.philox_normal_matrix(5, 3, 1 << 16, 0, rows=8, cols=12, row0=r * 8) for r in range(2)]
+    assert np.array_equal(np.concatenate(parts), full)

@@ -1,0 +1,248 @@
+"""GPU parity tests of the mlp.lua / main.lua:28-40 path through the C ABI (pytest -m gpu).
+
+The fused minibatch draws its noise on the device (Philox); the tests dump exactly that noise
+through vbnn_layer_draw_noise and inject it into the CPU oracle, so both sides see identical
+epsilon / zeta.  Tolerances (relative Frobenius error per tensor): fp32 mode <= 2e-4 after
+optimiser steps (<= 1e-5 on accumulators); bf16-operand mode <= 3e-2 on accumulators and
+<= 1e-2 on parameters."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vbnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def cpu(t):
+    return t.detach().float().cpu().numpy()
+
+
+def build_pair(ctx, sizes, N, S, B, precision, reparam, seed=0, strict=True, vb_output=False, lr_mu=None):
+    import vbnn_b200
+    from vbnn_b200 import _lib as L
+    over = dict(input_size=sizes[0], hidden=list(sizes[1:-1]), classes=[str(i) for i in range(sizes[-1])],
+                S=S, B=B, batchSize=N, testBatchSize=N, mu_init=1, var_init=0.01, reparam=reparam,
+                strict_reference=strict, vb_output=vb_output, log=False)
+    if lr_mu:
+        over["meanState"] = dict(learningRate=lr_mu)
+    gopt = vbnn_b200.default_opt(precision=precision, **over)
+    net = vbnn_b200.MLP(gopt, ctx, max_batch=N)
+    oopt = O.default_opt(**over)
+    ref = O.MLPOracle(oopt, torch.float64, seed=3)
+    rng = np.random.RandomState(seed)
+    layers = ref.vb + [ref.out]
+    for k, (gl, ol) in enumerate(zip(net.model, layers)):
+        if isinstance(ol, O.VBLinearOracle):
+            mu = rng.randn(ol.O, ol.I) * math.sqrt(2.0 / ol.I)
+            lv = rng.uniform(math.log(1e-4), math.log(1e-2), (ol.O, ol.I))
+            ol.means.copy_(torch.from_numpy(mu)); ol.lvars.copy_(torch.from_numpy(lv))
+            ol.compute_prior()
+            gl.set(L.BUF_MEANS, mu); gl.set(L.BUF_LVARS, lv)
+            gl.compute_prior()
+        else:
+            w = rng.randn(ol.weight.shape[0], ol.weight.shape[1]) * math.sqrt(2.0 / ol.weight.shape[1])
+            ol.weight.copy_(torch.from_numpy(w)); ol.bias.zero_()
+            gl.set(L.BUF_WEIGHT, w)
+    return net, ref, gopt, oopt
+
+
+def oracle_step(ref, oopt, X, T, eps=None, zeta=None):
+    """train_minibatch with the raw accumulators captured before update() rescales them in place."""
+    ref.resetGradients()
+    serr = sacc = 0.0
+    for s in range(oopt["S"]):
+        ref.sample(None if eps is None else eps[s])
+        e, a = ref.run(X, T, None if zeta is None else zeta[s])
+        serr += e; sacc += a
+    acc = [(l.gradWeight.clone(), l.gradSum.clone(), l.gradBias.clone()) for l in ref.vb_all]
+    ref.update(oopt)
+    return serr / oopt["S"], sacc / oopt["S"], acc
+
+
+def test_mlp_piecewise_against_golden(ctx):
+    """resetGradients / sample / run / update with the fixture's epsilon injected (fp32 mode)."""
+    import vbnn_b200
+    from vbnn_b200 import _lib as L
+    g = np.load(os.path.join(GOLD, "mlp_weight.npz"))
+    sizes = [int(v) for v in g["sizes"]]
+    opt = vbnn_b200.default_opt(input_size=sizes[0], hidden=sizes[1:-1], classes=list("abcde"), S=int(g["S"]),
+                                B=float(g["B"]), batchSize=int(g["N"]), mu_init=1, var_init=0.01, log=False)
+    net = vbnn_b200.MLP(opt, ctx, max_batch=int(g["N"]))
+    for k in range(2):
+        net.model[k].set(L.BUF_MEANS, g[f"means0_{k}"]); net.model[k].set(L.BUF_LVARS, g[f"lvars0_{k}"])
+        net.model[k].compute_prior()
+    net.model[2].set(L.BUF_WEIGHT, g["wout0"]); net.model[2].set(L.BUF_BIAS, g["bout0"])
+    for it in range(int(g["steps"])):
+        X = torch.from_numpy(g[f"X_{it}"]).float().cuda()
+        T = torch.from_numpy(g[f"T_{it}"]).float().cuda()
+        net.resetGradients()
+        serr = sacc = 0.0
+        for s in range(opt["S"]):
+            for k in range(2):
+                net.model[k].sample(eps=torch.from_numpy(g[f"eps_{it}_{s}_{k}"]).float().cuda(), sample_idx=s)
+            err, acc = net.run(X, T)
+            serr += err; sacc += acc
+        net.update(opt)
+        assert abs(serr / opt["S"] - float(g[f"err_{it}"])) < 1e-4 * abs(float(g[f"err_{it}"]))
+        assert abs(sacc / opt["S"] - float(g[f"acc_{it}"])) < 1e-3
+    for k in range(2):
+        assert rel(cpu(net.model[k].means), g[f"means1_{k}"]) < 2e-4
+        assert rel(cpu(net.model[k].lvars), g[f"lvars1_{k}"]) < 2e-4
+        assert rel(cpu(net.model[k].bias), g[f"bias1_{k}"]) < 1e-4
+    assert rel(cpu(net.model[2].weight), g["wout1"]) < 1e-5
+    assert rel(cpu(net.model[2].bias), g["bout1"]) < 1e-4
+    assert abs(net.calc_lc() - float(g["lc"])) < 1e-3 * abs(float(g["lc"]))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("reparam,vb_output", [("weight", False), ("local", False), ("local", True), ("weight", True)])
+def test_fused_step_vs_oracle(ctx, precision, reparam, vb_output):
+    """vbnn_mlp_step (S samples batched per launch; CUDA graph from the 2nd minibatch on) against
+    the oracle fed with the device-drawn noise."""
+    sizes, N, S = [40, 48, 36, 6], 24, 3
+    net, ref, gopt, oopt = build_pair(ctx, sizes, N, S, 30.0, precision, reparam, vb_output=vb_output)
+    rng = np.random.RandomState(5)
+    tol_acc = 1e-5 if precision == "fp32" else 3e-2
+    tol_par = 2e-4 if precision == "fp32" else 1e-2
+    nvb = len(ref.vb_all)
+    gidx = lambda k: k if k < len(ref.vb) else len(net.model) - 1
+    for it in range(4):
+        Xn = rng.randn(N, sizes[0]); Tn = rng.randint(1, sizes[-1] + 1, N).astype(np.float64)
+        step = ctx.get_step()
+        noise = [[torch.from_numpy(cpu(net.model[gidx(k)].draw_noise(step, s, rows=N)).astype(np.float64))
+                  for k in range(nvb)] for s in range(S)]
+        err, acc = net.train_step(torch.from_numpy(Xn).float().cuda(), torch.from_numpy(Tn).float().cuda())
+        if reparam == "local":
+            rerr, racc, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), zeta=noise)
+        else:
+            rerr, racc, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), eps=noise)
+        assert ctx.get_step() == step + 1
+        assert abs(err - rerr) < (1e-4 if precision == "fp32" else 3e-2) * abs(rerr), (it, err, rerr)
+        if precision == "fp32":
+            assert abs(acc - racc) < 1e-3
+        for k, ol in enumerate(ref.vb_all):
+            gl = net.model[gidx(k)]
+            gw, gs, gb = accs[k]
+            assert rel(cpu(gl.gradWeight), gw.numpy()) < tol_acc, (it, k, "gW")
+            assert rel(cpu(gl.gradSum), gs.numpy()) < tol_acc * 2, (it, k, "gS")
+            assert rel(cpu(gl.gradBias), gb.numpy()) < tol_acc, (it, k, "gb")
+            assert rel(cpu(gl.means), ol.means.numpy()) < tol_par, (it, k, "means")
+            assert rel(cpu(gl.lvars), ol.lvars.numpy()) < tol_par, (it, k, "lvars")
+            assert rel(cpu(gl.bias), ol.bias.numpy()) < max(tol_par, 1e-4), (it, k, "bias")
+        if not vb_output:
+            assert rel(cpu(net.model[-1].weight), ref.out.weight.numpy()) < tol_par
+
+
+def test_graph_replay_equals_eager(ctx):
+    rng = np.random.RandomState(1)
+    X = torch.from_numpy(rng.randn(32, 40)).float().cuda()
+    T = torch.from_numpy(rng.randint(1, 7, 32).astype(np.float32)).cuda()
+    outs = []
+    for no_graph in ("1", "0"):
+        os.environ["VBNN_NO_GRAPH"] = no_graph
+        ctx.set_step(100)
+        net, _, _, _ = build_pair(ctx, [40, 48, 36, 6], 32, 2, 30.0, "fp32", "weight", seed=9)
+        res = [net.train_step(X, T) for _ in range(4)]
+        outs.append((res, cpu(net.model[0].means).copy(), cpu(net.model[1].lvars).copy()))
+    os.environ.pop("VBNN_NO_GRAPH", None)
+    (r0, m0, l0), (r1, m1, l1) = outs
+    assert np.allclose(np.array(r0), np.array(r1), rtol=1e-5, atol=1e-6)
+    assert rel(m1, m0) < 1e-6 and rel(l1, l0) < 1e-6
+
+
+def test_step_host_equals_step_device(ctx):
+    rng = np.random.RandomState(2)
+    Xh = torch.from_numpy(rng.randn(16, 40)).float().pin_memory()
+    Th = torch.from_numpy(rng.randint(1, 7, 16).astype(np.float32)).pin_memory()
+    res = []
+    for mode in ("dev", "host", "pipe"):
+        ctx.set_step(7)
+        net, _, _, _ = build_pair(ctx, [40, 48, 36, 6], 16, 2, 30.0, "fp32", "weight", seed=4)
+        if mode == "dev":
+            r = [net.train_step(Xh.cuda(), Th.cuda()) for _ in range(3)]
+        elif mode == "host":
+            r = [net.train_step_host(Xh, Th) for _ in range(3)]
+        else:
+            net.submit_host(Xh, Th); net.submit_host(Xh, Th)
+            r = [net.collect()]
+            net.submit_host(Xh, Th)
+            r += [net.collect(), net.collect()]
+        res.append((r, cpu(net.model[0].means).copy()))
+    for r, m in res[1:]:
+        assert np.allclose(np.array(r), np.array(res[0][0]), rtol=1e-5, atol=1e-6)
+        assert rel(m, res[0][1]) < 1e-6
+
+
+def test_mlp_test_map_and_sampled(ctx):
+    sizes, N = [40, 48, 36, 6], 20
+    net, ref, gopt, oopt = build_pair(ctx, sizes, N, 2, 30.0, "fp32", "weight", seed=3)
+    rng = np.random.RandomState(8)
+    Xn = rng.randn(N, 40); Tn = rng.randint(1, 7, N).astype(np.float64)
+    X, T = torch.from_numpy(Xn).float().cuda(), torch.from_numpy(Tn).float().cuda()
+    net.opt["quicktest"] = True; oopt["quicktest"] = True                 # mlp.lua:87-91
+    e, a = net.test(X, T)
+    re_, ra = ref.test(torch.from_numpy(Xn), torch.from_numpy(Tn))
+    assert abs(e - re_) < 1e-4 * abs(re_) and abs(a - ra) < 1e-3
+    net.opt["quicktest"] = False; oopt["quicktest"] = False               # mlp.lua:93-102
+    net.opt["testSamples"] = oopt["testSamples"] = 5
+    step = ctx.get_step()
+    eps = [[torch.from_numpy(cpu(net.model[k].draw_noise(step, (1 << 20) + s)).astype(np.float64)) for k in range(2)]
+           for s in range(5)]
+    e, a = net.test(X, T)
+    re_, ra = ref.test(torch.from_numpy(Xn), torch.from_numpy(Tn), eps_lists=eps)
+    assert abs(e - re_) < 1e-4 * abs(re_) and abs(a - ra) < 1e-3
+
+
+def test_c1_config_learns(ctx):
+    """BASELINE configs[0] shape (784-100-10, batch 100, S=1): the loss must go down."""
+    import vbnn_b200
+    opt = vbnn_b200.default_opt(hidden=[100], S=1, B=600.0, batchSize=100, mu_init=1, msr_init=True, log=False,
+                                meanState=dict(learningRate=0.003))
+    net = vbnn_b200.MLP(opt, ctx, max_batch=100)
+    net.init_params(seed=4, he_means=True)
+    rng = np.random.RandomState(0)
+    Xn = rng.randn(100, 784).astype(np.float32)
+    Tn = ((Xn @ rng.randn(784, 10)).argmax(1) + 1).astype(np.float32)
+    X, T = torch.from_numpy(Xn).cuda(), torch.from_numpy(Tn).cuda()
+    first = net.train_step(X, T)[0]
+    for _ in range(150):
+        last = net.train_step(X, T)
+    assert last[0] < 0.7 * first and last[1] > 50.0
+
+
+@pytest.mark.parametrize("sizes,N,S,reparam", [([784, 1200, 1200, 10], 1024, 10, "weight"),
+                                              ([1024, 1024, 1024, 1000], 2048, 1, "local")])
+def test_full_size_bf16_tensor_core_path_matches_fp32_path(ctx, sizes, N, S, reparam):
+    """BASELINE-size minibatch (C2; a C3-shaped net): the tcgen05 path and the fp32 CUDA-core path
+    (itself oracle-checked above) draw identical Philox noise, so their accumulators must agree
+    to bf16-operand accuracy."""
+    rng = np.random.RandomState(3)
+    X = torch.from_numpy(rng.randn(N, sizes[0])).float().cuda()
+    T = torch.from_numpy(rng.randint(1, sizes[-1] + 1, N).astype(np.float32)).cuda()
+    out = {}
+    for precision in ("fp32", "bf16"):
+        ctx.set_step(11)
+        net, _, _, _ = build_pair(ctx, sizes, N, S, 58.6, precision, reparam, seed=6, strict=False)
+        err, acc = net.train_step(X, T)
+        assert math.isfinite(err)
+        out[precision] = (err, [cpu(m.gradWeight).copy() for m in net.model],
+                          [cpu(m.gradSum).copy() for m in net.model[:-1]], [cpu(m.means).copy() for m in net.model[:-1]])
+        del net
+    assert abs(out["bf16"][0] - out["fp32"][0]) < 2e-2 * abs(out["fp32"][0])
+    for a, b in zip(out["bf16"][1], out["fp32"][1]):
+        assert rel(a, b) < 3e-2
+    for a, b in zip(out["bf16"][2], out["fp32"][2]):
+        assert rel(a, b) < 5e-2
+    for a, b in zip(out["bf16"][3], out["fp32"][3]):
+        assert rel(a, b) < 1e-2

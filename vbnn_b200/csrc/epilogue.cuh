@@ -1,0 +1,220 @@
+// epilogue.cuh -- the fused GEMM epilogues of the VBLinear hot path, shared by the tcgen05
+// tensor-core kernel (gemm_tc.cu) and the fp32 CUDA-core kernel (gemm_simt.cu).
+//
+// One "quad" = 4 consecutive output columns of one output row; col % 4 == 0 so that a quad is
+// exactly one Philox counter (philox.cuh).  What each mode replaces in the reference:
+//   EPI_FWD      nn.Linear:updateOutput bias add (addr) + nn.ReLU           (mlp.lua:19,27,77)
+//   EPI_FWD_LRT  local reparameterisation forward (not in the reference)
+//   EPI_DX       nn.Linear:updateGradInput + nn.ReLU backward               (mlp.lua:79)
+//   EPI_DX_LRT   A12 backward-data
+//   EPI_DW       VBLinear:accGradParameters: gradWeight += s*G^T X and
+//                gradSum += (G^T X) .* eps from ONE GEMM                    (VBLinear.lua:113-115)
+//   EPI_DW_LRT   A12 parameter gradients (two accumulators)
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace vbnn {
+
+enum EpiMode : int {
+  EPI_STORE = 0,
+  EPI_FWD = 1,
+  EPI_FWD_LRT = 2,
+  EPI_DX = 3,
+  EPI_DX_LRT = 4,
+  EPI_DW = 5,
+  EPI_DW_LRT = 6,
+};
+
+__host__ __device__ constexpr bool epi_is_dual(int mode) {
+  return mode == EPI_FWD_LRT || mode == EPI_DX_LRT || mode == EPI_DW_LRT;
+}
+// DW modes accumulate over the batch index z (MC samples) into one output.
+__host__ __device__ constexpr bool epi_z_accumulates(int mode) {
+  return mode == EPI_DW || mode == EPI_DW_LRT;
+}
+
+struct EpiParams {
+  int M, N;                  // logical output extent (rows, cols)
+  // generic outputs; "act" pointers are AT (float or bf16), selected by the kernel template
+  float* out_f32; int ld_f32; long long zs_f32;
+  void* out_act; void* out_act2; void* r_out; int ld_act; long long zs_act;
+  // inputs read by the epilogue
+  const float* bias;         // [N]               (FWD, FWD_LRT)
+  int relu;                  // apply ReLU        (FWD, FWD_LRT)
+  const void* xprev;         // AT [M x ld_x]     (DX: mask source; DX_LRT: X and mask source)
+  const void* rprev;         // AT [M x ld_x]     (DX_LRT: R of the previous layer, nullable)
+  int ld_x; long long zs_x;
+  int mask;                  // DX/DX_LRT: multiply by (xprev > 0)
+  const float* noise;        // injected eps [M x N] (DW) / zeta [M x N] (FWD_LRT); NULL -> Philox
+  long long zs_noise;
+  PhiloxStream ps;           // Philox stream (sample = ps.sample + z)
+  const uint32_t* step_ptr;  // device step counter (overrides ps.step when non-null)
+  int row0;                  // global row offset of this rank's shard (FWD_LRT zeta)
+  // DW outputs
+  float* gW; float* gS; int ld_g;
+  float scale;               // accGradParameters' scale
+  int accumulate;            // 0: first z overwrites (saves the memset), 1: always +=
+};
+
+template <typename AT> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec4<bf16> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<uint32_t*>(&a);
+    t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&v)[4], int nvalid, bool vec) {
+  if (vec && nvalid == 4) {
+    Vec4<T>::load(p, v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = j < nvalid ? to_f32(p[j]) : 0.f;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float (&v)[4], int nvalid, bool vec) {
+  if (vec && nvalid == 4) {
+    Vec4<T>::store(p, v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nvalid) p[j] = from_f32<T>(v[j]);
+  }
+}
+
+// Process one quad.  a1/a2: accumulator values (a2 only for dual modes).
+template <int MODE, typename AT>
+__device__ __forceinline__ void epi_quad(const EpiParams& p, int z, int row, int col,
+                                         const float (&a1)[4], const float (&a2)[4]) {
+  if (row >= p.M || col >= p.N) return;
+  const int nvalid = min(4, p.N - col);
+  const bool vec_act = (p.ld_act & 3) == 0;
+  const bool vec_f32 = (p.ld_f32 & 3) == 0;
+
+  if constexpr (MODE == EPI_STORE) {
+    store4<float>(p.out_f32 + z * p.zs_f32 + (long long)row * p.ld_f32 + col, a1, nvalid, vec_f32);
+  } else if constexpr (MODE == EPI_FWD) {
+    float y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float b = (p.bias != nullptr && j < nvalid) ? __ldg(p.bias + col + j) : 0.f;
+      y[j] = a1[j] + b;
+      if (p.relu) y[j] = fmaxf(y[j], 0.f);
+    }
+    if (p.out_f32)
+      store4<float>(p.out_f32 + z * p.zs_f32 + (long long)row * p.ld_f32 + col, y, nvalid, vec_f32);
+    if (p.out_act)
+      store4<AT>((AT*)p.out_act + z * p.zs_act + (long long)row * p.ld_act + col, y, nvalid, vec_act);
+  } else if constexpr (MODE == EPI_FWD_LRT) {
+    float zt[4];
+    if (p.noise) {
+      load4<float>(p.noise + z * p.zs_noise + (long long)row * p.N + col, zt, nvalid, (p.N & 3) == 0);
+    } else {
+      PhiloxStream ps = p.ps;
+      ps.sample += (uint32_t)z;
+      if (p.step_ptr) ps.step = *p.step_ptr;
+      uint32_t q = (uint32_t)((p.N + 3) >> 2);
+      philox_normal4(ps, (uint32_t)(row + p.row0) * q + (uint32_t)(col >> 2), zt);
+    }
+    float y[4], y2[4], r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float b = (p.bias != nullptr && j < nvalid) ? __ldg(p.bias + col + j) : 0.f;
+      float v = fmaxf(a2[j], 0.f);
+      float sq = sqrtf(v);
+      y[j] = a1[j] + b + sq * zt[j];
+      r[j] = sq > 0.f ? zt[j] / (2.f * sq) : 0.f;
+    }
+    if (p.out_f32)
+      store4<float>(p.out_f32 + z * p.zs_f32 + (long long)row * p.ld_f32 + col, y, nvalid, vec_f32);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (p.relu) y[j] = fmaxf(y[j], 0.f);
+      // square the value the next layer will actually read (after rounding to AT)
+      float yr = to_f32(from_f32<AT>(y[j]));
+      y2[j] = yr * yr;
+    }
+    long long off = z * p.zs_act + (long long)row * p.ld_act + col;
+    if (p.out_act) store4<AT>((AT*)p.out_act + off, y, nvalid, vec_act);
+    if (p.out_act2) store4<AT>((AT*)p.out_act2 + off, y2, nvalid, vec_act);
+    if (p.r_out) store4<AT>((AT*)p.r_out + off, r, nvalid, vec_act);
+  } else if constexpr (MODE == EPI_DX || MODE == EPI_DX_LRT) {
+    const bool vec_x = (p.ld_x & 3) == 0;
+    long long xoff = z * p.zs_x + (long long)row * p.ld_x + col;
+    float x[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.xprev) load4<AT>((const AT*)p.xprev + xoff, x, nvalid, vec_x);
+    float g[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      g[j] = a1[j];
+      if constexpr (MODE == EPI_DX_LRT) g[j] += 2.f * x[j] * a2[j];
+      if (p.mask) g[j] = x[j] > 0.f ? g[j] : 0.f;
+    }
+    if (p.out_f32)
+      store4<float>(p.out_f32 + z * p.zs_f32 + (long long)row * p.ld_f32 + col, g, nvalid, vec_f32);
+    long long off = z * p.zs_act + (long long)row * p.ld_act + col;
+    if (p.out_act) store4<AT>((AT*)p.out_act + off, g, nvalid, vec_act);
+    if (p.out_act2 && p.rprev) {
+      float r[4], h[4];
+      load4<AT>((const AT*)p.rprev + xoff, r, nvalid, vec_x);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = to_f32(from_f32<AT>(g[j])) * r[j];
+      store4<AT>((AT*)p.out_act2 + off, h, nvalid, vec_act);
+    }
+  } else if constexpr (MODE == EPI_DW || MODE == EPI_DW_LRT) {
+    const bool vec_g = (p.ld_g & 3) == 0;
+    long long goff = (long long)row * p.ld_g + col;
+    const bool acc = p.accumulate || z > 0;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (acc) load4<float>(p.gW + goff, w, nvalid, vec_g);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] += p.scale * a1[j];
+    store4<float>(p.gW + goff, w, nvalid, vec_g);
+    if (p.gS) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+      if (acc) load4<float>(p.gS + goff, s, nvalid, vec_g);
+      if constexpr (MODE == EPI_DW) {
+        float e[4];
+        if (p.noise) {
+          load4<float>(p.noise + z * p.zs_noise + (long long)row * p.N + col, e, nvalid, (p.N & 3) == 0);
+        } else {
+          PhiloxStream ps = p.ps;
+          ps.sample += (uint32_t)z;
+          if (p.step_ptr) ps.step = *p.step_ptr;
+          uint32_t q = (uint32_t)((p.N + 3) >> 2);
+          philox_normal4(ps, (uint32_t)row * q + (uint32_t)(col >> 2), e);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += a1[j] * e[j];     // VBLinear.lua:115 (ignores scale)
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] += a2[j];
+      }
+      store4<float>(p.gS + goff, s, nvalid, vec_g);
+    }
+  }
+}
+
+}  // namespace vbnn

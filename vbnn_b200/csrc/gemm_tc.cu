@@ -1,0 +1,489 @@
+// gemm_tc.cu -- bf16 x bf16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05), sm_100a only.
+//
+// The dense work of the VBLinear hot path (reference call sites: nn.Linear:updateOutput /
+// updateGradInput via mlp.lua:77,79 and VBLinear:accGradParameters VBLinear.lua:113-115, all of
+// which reach cublasSgemm in the reference) as ONE warp-specialised persistent kernel:
+//
+//   warp 0        TMA producer   cp.async.bulk.tensor (128B-swizzled boxes) -> smem ring
+//   warp 1        MMA issuer     tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM
+//   warps 2..9    epilogue       tcgen05.ld TMEM -> registers -> fused VB epilogue (epilogue.cuh)
+//
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue,
+// two accumulator stages so tile i's epilogue overlaps tile i+1's MMAs), and a static
+// round-robin tile scheduler (grid = #SMs).  The "dual" modes (local reparameterisation) run
+// two GEMMs with different operands into two TMEM accumulators and join them in the epilogue.
+//
+// Operands may be K-major or MN-major in global memory; MN-major tiles are fetched as
+// {64 x BK} boxes and handed to the MMA through an MN-major shared-memory descriptor, so the
+// batch-contracting dW GEMM (D = G^T X) and dX = G W need no transposed copies.
+#include "gemm.h"
+
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace vbnn {
+
+namespace {
+
+constexpr int BM = 128;   // UMMA M (cta_group::1)
+constexpr int BK = 64;    // one 128-byte swizzle row of bf16
+constexpr int UK = 16;    // UMMA K for 16-bit inputs
+constexpr int EPIW = 8;   // epilogue warps
+constexpr int NTHREADS = (2 + EPIW) * 32;
+constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // minus barriers + alignment slack
+
+// ------------------------------------------------------------------ PTX wrappers ---------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
+// Bounded wait: a protocol bug traps (the launch fails) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("vbnn gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
+                                            int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread t gets lane (base_lane + t), columns col..col+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- UMMA shared-memory descriptor (SWIZZLE_128B) ---------------------------------------------
+// bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
+// K-major  tile [rows x 64]: 8-row groups of 128-byte rows, SBO = 1024, LBO unused (=16 B);
+//          the k-th UMMA_K slice starts 32 bytes further along the swizzled row.
+// MN-major tile [64 k-rows x 64*c]: each k-row is 128 bytes of 64 MN elements, 8 k-rows = one
+//          1024-byte swizzle atom (SBO), the next 64-wide MN chunk is a separate TMA box LBO =
+//          BK*128 bytes away; the k-th UMMA_K slice starts 16 rows = 2048 bytes further.
+template <bool KMAJOR>
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
+  constexpr uint64_t lbo = KMAJOR ? 16 : (uint64_t)BK * 128;
+  constexpr uint64_t sbo = 1024;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (lbo >> 4) << 16;
+  d |= (sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+template <bool KMAJOR>
+__device__ __forceinline__ constexpr uint32_t kslice_bytes() {
+  return KMAJOR ? UK * 2 : UK * 128;
+}
+// instruction descriptor: c=F32 [4,6), a=b=BF16 [7,10),[10,13), a_major 15, b_major 16,
+// N>>3 [17,23), M>>4 [24,29)
+template <int BN, bool AK, bool BKM>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((AK ? 0u : 1u) << 15) | ((BKM ? 0u : 1u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcShape {
+  int M, N, K, batch;
+  int mt, nt, num_kb;
+  int zA1, zB1, zA2, zB2;   // 0: the operand is shared by every batch index z (stride 0), 1: batched
+};
+
+template <int MODE, int BN>
+struct TcCfg {
+  static constexpr bool DUAL = epi_is_dual(MODE);
+  static constexpr int NACC = DUAL ? 2 : 1;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = NACC * (A_BYTES + B_BYTES);
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int ACC_COLS = NACC * BN;        // TMEM columns per accumulator stage
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;    // double-buffered
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+  static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
+};
+
+// One operand tile: K-major -> one {64 x ROWS} box; MN-major -> ROWS/64 boxes of {64 x BK}.
+template <bool KMAJOR, int ROWS>
+__device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, uint32_t bar,
+                                             int mn0, int k0, int z) {
+  if constexpr (KMAJOR) {
+    tma_load_3d(dst, tm, bar, k0, mn0, z);
+  } else {
+#pragma unroll
+    for (int c = 0; c < ROWS / 64; ++c) tma_load_3d(dst + c * (BK * 128), tm, bar, mn0 + c * 64, k0, z);
+  }
+}
+
+template <int MODE, int BN, bool AK, bool BKM>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               TcShape sh, EpiParams p) {
+  using C = TcCfg<MODE, BN>;
+  constexpr bool DUAL = C::DUAL;
+  constexpr bool ZACC = epi_z_accumulates(MODE);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM address
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB1);
+    if (DUAL) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPIW); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles = sh.mt * sh.nt;
+  const int num_work = ZACC ? tiles : tiles * sh.batch;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = ZACC ? w : w % tiles;
+        const int zb = ZACC ? 0 : w / tiles, zn = ZACC ? sh.batch : 1;
+        const int m0 = (tile % sh.mt) * BM, n0 = (tile / sh.mt) * BN;
+        for (int z = zb; z < zb + zn; ++z) {
+          for (int kb = 0; kb < sh.num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+            const uint32_t sb = sa + C::NACC * C::A_BYTES;
+            load_operand<AK, BM>(&tmA1, sa, full_bar(stage), m0, kb * BK, z * sh.zA1);
+            load_operand<BKM, BN>(&tmB1, sb, full_bar(stage), n0, kb * BK, z * sh.zB1);
+            if (DUAL) {
+              load_operand<AK, BM>(&tmA2, sa + C::A_BYTES, full_bar(stage), m0, kb * BK, z * sh.zA2);
+              load_operand<BKM, BN>(&tmB2, sb + C::B_BYTES, full_bar(stage), n0, kb * BK, z * sh.zB2);
+            }
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (one thread) =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN, AK, BKM>();
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int zn = ZACC ? sh.batch : 1;
+        for (int zi = 0; zi < zn; ++zi) {
+          mbar_wait(tempty_bar(as), aphase ^ 1);
+          tc_fence_after();
+          const uint32_t d1 = tmem_base + as * C::ACC_COLS;
+          for (int kb = 0; kb < sh.num_kb; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+            const uint32_t sb = sa + C::NACC * C::A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+              umma_bf16(d1, make_sdesc<AK>(sa + k * kslice_bytes<AK>()),
+                        make_sdesc<BKM>(sb + k * kslice_bytes<BKM>()), idesc, acc);
+              if (DUAL)
+                umma_bf16(d1 + BN, make_sdesc<AK>(sa + C::A_BYTES + k * kslice_bytes<AK>()),
+                          make_sdesc<BKM>(sb + C::B_BYTES + k * kslice_bytes<BKM>()), idesc, acc);
+            }
+            tc_commit(empty_bar(stage));     // smem slot free once these MMAs retire
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(tfull_bar(as));          // accumulator ready for the epilogue
+          if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ======================= epilogue warps =======================
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;        // two warps share a quarter, split the columns
+    int as = 0; uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int tile = ZACC ? w : w % tiles;
+      const int zb = ZACC ? 0 : w / tiles, zn = ZACC ? sh.batch : 1;
+      const int m0 = (tile % sh.mt) * BM, n0 = (tile / sh.mt) * BN;
+      const int row = m0 + q * 32 + lane;
+      for (int z = zb; z < zb + zn; ++z) {
+        mbar_wait(tfull_bar(as), aphase);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS;
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += EPIW / 4) {
+          if (n0 + c * 32 >= sh.N) break;    // warp-uniform
+          float v1[32], v2[32];
+          tmem_ld32(t0 + c * 32, v1);
+          if (DUAL) tmem_ld32(t0 + BN + c * 32, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            epi_quad<MODE, bf16>(p, z, row, n0 + c * 32 + j * 4,
+                                 *reinterpret_cast<const float(*)[4]>(&v1[j * 4]),
+                                 *reinterpret_cast<const float(*)[4]>(&v2[DUAL ? j * 4 : 0]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side -------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+      qr != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// rows_mn: MN extent, K: contraction extent, box_mn: tile rows for a K-major operand
+int make_tmap(CUtensorMap* tm, const TcOperand& op, int rows_mn, int K, int batch, int box_mn) {
+  PFN_encodeTiled enc = get_encode();
+  VB_CHECK(enc != nullptr, VBNN_E_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  VB_CHECK(op.ptr != nullptr, VBNN_E_INVALID, "gemm_tc: null operand");
+  VB_CHECK((op.ld % 8) == 0 && (reinterpret_cast<uintptr_t>(op.ptr) % 16) == 0, VBNN_E_INVALID,
+           "gemm_tc: operand rows must be 16-byte aligned (ld=%d)", op.ld);
+  VB_CHECK(batch == 1 || (op.zs % 8) == 0, VBNN_E_INVALID, "gemm_tc: batch stride %% 8 != 0");
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  if (op.kmajor) {
+    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows_mn;
+    box[0] = BK; box[1] = (cuuint32_t)box_mn;
+  } else {
+    dims[0] = (cuuint64_t)rows_mn; dims[1] = (cuuint64_t)K;
+    box[0] = 64; box[1] = BK;
+  }
+  const bool batched = batch > 1 && op.zs != 0;
+  dims[2] = batched ? (cuuint64_t)batch : 1;
+  box[2] = 1;
+  strides[0] = (cuuint64_t)op.ld * 2;
+  strides[1] = batched ? (cuuint64_t)op.zs * 2 : strides[0] * dims[1];
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(op.ptr), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VB_CHECK(r == CUDA_SUCCESS, VBNN_E_CUDA,
+           "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu ld %d kmajor %d", (int)r,
+           (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+           op.ld, op.kmajor);
+  return VBNN_OK;
+}
+
+int g_block_n_override = 0;
+
+template <int MODE, int BN, bool AK, bool BKM>
+int launch_cfg(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
+  using C = TcCfg<MODE, BN>;
+  TcShape sh;
+  sh.M = g.M; sh.N = g.N; sh.K = g.K; sh.batch = g.batch;
+  sh.mt = ceil_div(g.M, BM); sh.nt = ceil_div(g.N, BN); sh.num_kb = ceil_div(g.K, BK);
+  sh.zA1 = g.A1.zs != 0; sh.zB1 = g.B1.zs != 0; sh.zA2 = g.A2.zs != 0; sh.zB2 = g.B2.zs != 0;
+  CUtensorMap tA1, tB1, tA2, tB2;
+  VB_TRY(make_tmap(&tA1, g.A1, g.M, g.K, g.batch, BM));
+  VB_TRY(make_tmap(&tB1, g.B1, g.N, g.K, g.batch, BN));
+  if (C::DUAL) {
+    VB_TRY(make_tmap(&tA2, g.A2, g.M, g.K, g.batch, BM));
+    VB_TRY(make_tmap(&tB2, g.B2, g.N, g.K, g.batch, BN));
+  } else {
+    tA2 = tA1; tB2 = tB1;
+  }
+  auto kern = gemm_tc_kernel<MODE, BN, AK, BKM>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = sh.mt * sh.nt;
+  const int num_work = epi_z_accumulates(MODE) ? tiles : tiles * g.batch;
+  int dev = 0, sms = kNumSMs;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = num_work < sms ? num_work : sms;
+  kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(tA1, tB1, tA2, tB2, sh, p);
+  VB_CUDA(cudaGetLastError());
+  return VBNN_OK;
+}
+
+// Pick BLOCK_N for the single-accumulator modes: the wider tile halves the per-flop smem/L2
+// traffic, the narrower one quantises better on small problems.
+template <int MODE, bool AK, bool BKM>
+int launch_single(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
+  int bn = g_block_n_override;
+  if (bn == 0) {
+    const char* env = getenv("VBNN_TC_BN");      // debugging knob (tools/gemm_probe.py)
+    if (env) bn = atoi(env);
+  }
+  if (bn != 128 && bn != 256) bn = 0;
+  if (bn == 0) {
+    const int mt = ceil_div(g.M, BM);
+    const long long zmul = epi_z_accumulates(MODE) ? 1 : g.batch;
+    const long long w256 = (long long)mt * ceil_div(g.N, 256) * zmul;
+    const long long w128 = (long long)mt * ceil_div(g.N, 128) * zmul;
+    // waves * tile cost (256-wide tile costs 2 units)
+    const long long c256 = ((w256 + kNumSMs - 1) / kNumSMs) * 2;
+    const long long c128 = ((w128 + kNumSMs - 1) / kNumSMs) * 1;
+    bn = (g.N > 128 && c256 <= c128) ? 256 : 128;
+  }
+  if (bn == 256) return launch_cfg<MODE, 256, AK, BKM>(g, p, st);
+  return launch_cfg<MODE, 128, AK, BKM>(g, p, st);
+}
+
+}  // namespace
+
+void gemm_tc_set_debug(int block_n_override) { g_block_n_override = block_n_override; }
+
+int gemm_tc_launch(int mode, const TcGemmArgs& g, const EpiParams& p, cudaStream_t st,
+                   long long* launches) {
+  VB_CHECK(g.M > 0 && g.N > 0 && g.K > 0 && g.batch > 0, VBNN_E_INVALID,
+           "gemm_tc: empty problem %d x %d x %d (batch %d)", g.M, g.N, g.K, g.batch);
+  if (launches) *launches += 1;
+  const bool ak = g.A1.kmajor != 0, bk = g.B1.kmajor != 0;
+  switch (mode) {
+    case EPI_STORE:
+      if (ak && bk) return launch_single<EPI_STORE, true, true>(g, p, st);
+      if (ak && !bk) return launch_single<EPI_STORE, true, false>(g, p, st);
+      if (!ak && bk) return launch_single<EPI_STORE, false, true>(g, p, st);
+      return launch_single<EPI_STORE, false, false>(g, p, st);
+    case EPI_FWD:
+      VB_CHECK(ak && bk, VBNN_E_INVALID, "EPI_FWD expects K-major operands");
+      return launch_single<EPI_FWD, true, true>(g, p, st);
+    case EPI_FWD_LRT:
+      VB_CHECK(ak && bk, VBNN_E_INVALID, "EPI_FWD_LRT expects K-major operands");
+      return launch_cfg<EPI_FWD_LRT, 128, true, true>(g, p, st);
+    case EPI_DX:
+      VB_CHECK(ak && !bk, VBNN_E_INVALID, "EPI_DX expects K-major A, MN-major B");
+      return launch_single<EPI_DX, true, false>(g, p, st);
+    case EPI_DX_LRT:
+      VB_CHECK(ak && !bk, VBNN_E_INVALID, "EPI_DX_LRT expects K-major A, MN-major B");
+      return launch_cfg<EPI_DX_LRT, 128, true, false>(g, p, st);
+    case EPI_DW:
+      VB_CHECK(!ak && !bk, VBNN_E_INVALID, "EPI_DW expects MN-major operands");
+      return launch_single<EPI_DW, false, false>(g, p, st);
+    case EPI_DW_LRT:
+      VB_CHECK(!ak && !bk, VBNN_E_INVALID, "EPI_DW_LRT expects MN-major operands");
+      return launch_cfg<EPI_DW_LRT, 128, false, false>(g, p, st);
+  }
+  set_error("gemm_tc_launch: bad mode %d", mode);
+  return VBNN_E_INVALID;
+}
+
+}  // namespace vbnn

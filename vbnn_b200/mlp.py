@@ -1,0 +1,176 @@
+"""The mlp.lua net object (reference mlp.lua:5-143) over libvbnn.so: buildModel, resetGradients,
+sample, run, test, calc_lc, update -- same names and order as the reference so that a
+main.lua-style loop drives it unchanged -- plus the fused per-minibatch entry points
+(train_step / train_step_host) that keep minibatches, weights and noise on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib as L
+from .config import opts_struct
+from .context import Context, as_dev_f32, default_context
+from .vblinear import Linear, VBLinear
+
+
+class MLP:
+    def __init__(self, opt=None, ctx: Context = None, max_batch=None):
+        self.handle = None
+        if opt is not None:
+            self.buildModel(opt, ctx, max_batch)
+
+    # ---- mlp.lua:7-60 ----
+    def buildModel(self, opt, ctx: Context = None, max_batch=None):
+        self.opt = opt
+        self.ctx = ctx or default_context(seed=opt.get("seed", 3))
+        sizes = [int(opt["input_size"])] + [int(h) for h in opt["hidden"]] + [len(opt["classes"])]
+        self.sizes = sizes
+        self.max_batch = int(max_batch or max(opt["batchSize"], opt.get("testBatchSize", 1)))
+        arr = (C.c_int * len(sizes))(*sizes)
+        o = opts_struct(opt)
+        self.handle = C.c_void_p()
+        L.check(L.lib().vbnn_mlp_create(self.ctx.handle, arr, len(sizes), 1 if opt.get("vb_output") else 0,
+                                        self.max_batch, C.byref(o), C.byref(self.handle)))
+        self.model = []
+        self.vb_indices = []                                            # mlp.lua:9,15,23
+        n = L.lib().vbnn_mlp_num_layers(self.handle)
+        for k in range(n):
+            h = C.c_void_p()
+            L.check(L.lib().vbnn_mlp_layer(self.handle, k, C.byref(h)))
+            vb = k < n - 1 or opt.get("vb_output")
+            cls = VBLinear if vb else Linear
+            self.model.append(cls(sizes[k], sizes[k + 1], opt, self.ctx, _borrowed=h))
+            if vb:
+                self.vb_indices.append(k)
+        self._s = 0
+        return self
+
+    def init_params(self, seed=4, he_means=False):
+        """means per VBLinear.lua:22-29 (or He-scaled), Linear weights N(0, 2/fan_in)
+        and zero biases per mlp.lua:47-55, drawn on the device."""
+        L.check(L.lib().vbnn_mlp_init_params(self.handle, C.c_uint64(seed), 1 if he_means else 0))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                for m in self.model:
+                    m.handle = None
+                L.lib().vbnn_mlp_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _io(self, inputs, targets):
+        x = as_dev_f32(inputs, self.ctx.device)
+        x = x.reshape(x.shape[0], -1)                                   # nn.Reshape (mlp.lua:12)
+        t = as_dev_f32(targets, self.ctx.device).reshape(-1)
+        if x.shape[1] != self.sizes[0] or t.shape[0] != x.shape[0]:
+            raise L.VbnnError(L.E_INVALID, f"inputs must be [N x {self.sizes[0]}] with N targets")
+        return x, t
+
+    # ---- mlp.lua:62-84 ----
+    def resetGradients(self):
+        L.check(L.lib().vbnn_mlp_reset_gradients(self.handle))
+        self._s = 0
+
+    def sample(self, sample_idx=None):
+        if sample_idx is not None:
+            self._s = int(sample_idx)
+        L.check(L.lib().vbnn_mlp_sample(self.handle, self._s))
+        self._cur = self._s
+        self._s += 1
+
+    def run(self, inputs, targets):
+        x, t = self._io(inputs, targets)
+        err, acc = C.c_float(), C.c_float()
+        s = getattr(self, "_cur", 0)
+        if self.opt.get("reparam", "weight") == "local":
+            s = self._s
+            self._s += 1
+        L.check(L.lib().vbnn_mlp_run(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
+                                     x.shape[0], s, C.byref(err), C.byref(acc)))
+        return err.value, acc.value
+
+    # ---- mlp.lua:86-107 ----
+    def test(self, input, target):
+        x, t = self._io(input, target)
+        err, acc = C.c_float(), C.c_float()
+        ns = 0 if self.opt.get("quicktest") else int(self.opt["testSamples"])
+        L.check(L.lib().vbnn_mlp_test(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
+                                      x.shape[0], ns, C.byref(err), C.byref(acc)))
+        return err.value, acc.value
+
+    def calc_lc(self, opt=None):                                        # mlp.lua:109-115
+        v = C.c_float()
+        L.check(L.lib().vbnn_mlp_calc_lc(self.handle, C.byref(v)))
+        return v.value
+
+    def update(self, opt=None):                                         # mlp.lua:117-142
+        L.check(L.lib().vbnn_mlp_update(self.handle))
+
+    # ---- fused minibatch: main.lua:28-40 in one call ----
+    def train_step(self, inputs, targets, sync=True):
+        """inputs/targets already on the device.  Returns (error, accuracy) averaged over the S
+        samples as main.lua:38-39 (or None when sync=False)."""
+        import torch
+        x, t = self._io(inputs, targets)
+        if not hasattr(self, "_res"):
+            self._res = torch.zeros(2, dtype=torch.float32, device=x.device)
+        L.check(L.lib().vbnn_mlp_step(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
+                                      x.shape[0], C.c_void_p(self._res.data_ptr())))
+        if not sync:
+            return None
+        r = self._res.cpu()
+        return float(r[0]), float(r[1])
+
+    def train_step_host(self, inputs_host, targets_host):
+        """HOST buffers in, host scalars out: H2D and D2H inside the call (main.lua:23-24)."""
+        x, t = self._host_io(inputs_host, targets_host)
+        err, acc = C.c_float(), C.c_float()
+        L.check(L.lib().vbnn_mlp_step_host(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
+                                           x.shape[0], C.byref(err), C.byref(acc)))
+        return err.value, acc.value
+
+    def _host_io(self, inputs_host, targets_host):
+        import torch
+        x = torch.as_tensor(inputs_host, dtype=torch.float32)
+        t = torch.as_tensor(targets_host, dtype=torch.float32)
+        if x.is_cuda or t.is_cuda:
+            raise L.VbnnError(L.E_INVALID, "train_step_host expects host tensors")
+        x = x.reshape(x.shape[0], -1).contiguous()
+        return x, t.reshape(-1).contiguous()
+
+    def submit_host(self, inputs_host, targets_host):
+        x, t = self._host_io(inputs_host, targets_host)
+        self._keep = getattr(self, "_keep", [])
+        self._keep.append((x, t))
+        self._keep = self._keep[-4:]
+        L.check(L.lib().vbnn_mlp_submit_host(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
+                                             x.shape[0]))
+
+    def collect(self):
+        err, acc = C.c_float(), C.c_float()
+        L.check(L.lib().vbnn_mlp_collect(self.handle, C.byref(err), C.byref(acc)))
+        return err.value, acc.value
+
+    def outputs(self, sample_idx=0, n=None):
+        """LogSoftMax output of the last forward (self.model.output in the reference)."""
+        import torch
+        n = n or self._last_n()
+        out = torch.empty(n, self.sizes[-1], dtype=torch.float32)
+        L.check(L.lib().vbnn_mlp_get_outputs(self.handle, sample_idx, C.c_void_p(out.data_ptr())))
+        return out
+
+    def _last_n(self):
+        return self.max_batch
+
+    def launch_count(self):
+        v = C.c_longlong()
+        L.check(L.lib().vbnn_mlp_launch_count(self.handle, C.byref(v)))
+        return v.value
+
+    def grad_arena(self):
+        import torch
+        from .context import DevView
+        p, n = C.c_void_p(), C.c_size_t()
+        L.check(L.lib().vbnn_mlp_grad_arena(self.handle, C.byref(p), C.byref(n)))
+        return torch.as_tensor(DevView(p.value, (n.value,)), device=f"cuda:{self.ctx.device}")
