@@ -1,0 +1,76 @@
+-- vbnn_ffi.lua -- LuaJIT FFI declarations of libvbnn.so (include/vbnn.h), the part the shim uses.
+-- NOT EXECUTED IN THIS REPO'S CI: the build image and the GPU box have no Lua/LuaJIT/Torch7
+-- (SURVEY.md section 8c).  The same ABI is exercised through Python ctypes (vbnn_b200/_lib.py)
+-- and the tests in tests/; this file is the binding a VBNN maintainer would drop in.
+local ffi = require 'ffi'
+
+ffi.cdef[[
+typedef struct vbnn_ctx vbnn_ctx;
+typedef struct vbnn_layer vbnn_layer;
+typedef struct vbnn_opts {
+  float var_init; int msr_init; float mu_init; float B; int S;
+  float lr_bias, lr_mu, lr_var; float adam_beta1, adam_beta2, adam_eps;
+  int reparam; int precision; int strict_reference;
+} vbnn_opts;
+typedef struct vbnn_stats {
+  float vlc_grad, vle_grad, mlc_grad, mle_grad, min_variance, max_variance, mean_variance, var_hat;
+  float mean_means, std_means, min_means, max_means, mu_normratio, var_normratio;
+} vbnn_stats;
+const char* vbnn_last_error(void);
+void vbnn_opts_default(vbnn_opts*);
+int vbnn_ctx_create(int device, void* stream, uint64_t seed, vbnn_ctx** out);
+int vbnn_ctx_destroy(vbnn_ctx*);
+int vbnn_layer_create(vbnn_ctx*, int inputSize, int outputSize, int kind, const vbnn_opts*, vbnn_layer** out);
+int vbnn_layer_destroy(vbnn_layer*);
+int vbnn_layer_sample(vbnn_layer*, int sample_idx, const float* eps_dev);
+int vbnn_layer_clamp_to_map(vbnn_layer*);
+int vbnn_layer_forward(vbnn_layer*, const float* X_dev, int N, float* Y_dev, const float* zeta_dev);
+int vbnn_layer_backward_data(vbnn_layer*, const float* X_dev, const float* G_dev, int N, float* dX_dev);
+int vbnn_layer_acc_grad(vbnn_layer*, const float* X_dev, const float* G_dev, int N, float scale);
+int vbnn_layer_reset_acc(vbnn_layer*);
+int vbnn_layer_compute_prior(vbnn_layer*, float* mu_hat, float* var_hat);
+int vbnn_layer_grads(vbnn_layer*, float* mleg, float* mlcg, float* vleg, float* vlcg);
+int vbnn_layer_update(vbnn_layer*, vbnn_stats*);
+int vbnn_layer_calc_lc(vbnn_layer*, float* lc_dev, float* sum_host);
+int vbnn_layer_device_ptr(vbnn_layer*, int which, float** ptr_dev, size_t* count);
+]]
+
+local C = ffi.load('vbnn')
+
+local M = { C = C, ffi = ffi }
+
+function M.check(rc)
+   if rc ~= 0 then error('libvbnn: ' .. ffi.string(C.vbnn_last_error()), 2) end
+end
+
+-- one context per process, on cutorch's current device and stream
+function M.context(seed)
+   if not M.ctx then
+      local out = ffi.new('vbnn_ctx*[1]')
+      local dev = cutorch.getDevice() - 1
+      local stream = cutorch.getStream and cutorch._state and nil or nil  -- NULL: private stream
+      M.check(C.vbnn_ctx_create(dev, stream, seed or 3, out))
+      M.ctx = ffi.gc(out[0], C.vbnn_ctx_destroy)
+   end
+   return M.ctx
+end
+
+function M.opts(opt)
+   local o = ffi.new('vbnn_opts')
+   C.vbnn_opts_default(o)
+   o.var_init = opt.var_init; o.msr_init = opt.msr_init and 1 or 0; o.mu_init = opt.mu_init
+   o.B = opt.B; o.S = opt.S
+   o.lr_bias = opt.state.learningRate; o.lr_mu = opt.meanState.learningRate; o.lr_var = opt.varState.learningRate
+   o.reparam = (opt.reparam == 'local') and 1 or 0
+   o.precision = (opt.precision == 'bf16') and 1 or 0
+   o.strict_reference = (opt.strict_reference == false) and 0 or 1
+   return o
+end
+
+-- raw device pointer of a CudaTensor (contiguous, float)
+function M.ptr(t)
+   assert(t:isContiguous(), 'libvbnn needs contiguous tensors')
+   return ffi.cast('float*', torch.pointer(t:storage():data()) + 0) + (t:storageOffset() - 1)
+end
+
+return M

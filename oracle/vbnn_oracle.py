@@ -24,6 +24,12 @@ What is restated (reference file:line):
                                   formulas restated from the north star and verified
                                   against torch fp64 autograd in tests/test_oracle.py
 
+``operand_round`` (default: identity) restates the tensor-core path's operand staging: the
+function is applied exactly where libvbnn's VBNN_PREC_BF16 mode rounds a GEMM operand to bf16
+(sampled weights, mu / sigma^2 copies, activations, X^2, R, back-propagated gradients); every
+accumulation stays in the oracle's dtype, as the GPU accumulates in fp32.  With it the bf16 GPU
+path is checked to ~1e-3; without it the same tests state the bf16-vs-fp64 gap separately.
+
 All arithmetic is torch-CPU in the dtype given at construction (float64 for the
 checker, float32 + 8 threads for the timed "reference CPU path").  Noise is
 always injectable so that the CUDA path and the oracle see identical epsilon.
@@ -78,6 +84,15 @@ def default_opt(**over):
 # Both return (x, applied_step) -- quirk Q5: the reference reads a third return
 # value "update"; we define it as x_new - x_old.
 # ----------------------------------------------------------------------------
+def round_bf16(x: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest-even to bfloat16 and back: the operand_round of VBNN_PREC_BF16."""
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+def _ident(x):
+    return x
+
+
 def optim_sgd(x: torch.Tensor, dfdx: torch.Tensor, state: dict):
     lr = state.get("learningRate", 1e-3)
     lrd = state.get("learningRateDecay", 0.0)
@@ -116,10 +131,11 @@ def optim_adam(x: torch.Tensor, dfdx: torch.Tensor, state: dict):
 # ----------------------------------------------------------------------------
 class VBLinearOracle:
     def __init__(self, inputSize: int, outputSize: int, opt: dict,
-                 dtype=torch.float64, rng: Optional[np.random.RandomState] = None):
+                 dtype=torch.float64, rng: Optional[np.random.RandomState] = None, operand_round=None):
         # VBLinear.lua:9-47
         self.opt = opt
         self.dtype = dtype
+        self.q = operand_round or _ident
         self.I, self.O = inputSize, outputSize
         rng = rng or np.random.RandomState(3)               # config.lua:40 manualSeed(3)
         self.rng = rng
@@ -160,7 +176,7 @@ class VBLinearOracle:
         else:
             stdv = torch.exp(0.5 * self.lvars)
         w = self.means + stdv * self.e                      # :59
-        self.weight.copy_(w)                                # :63
+        self.weight.copy_(self.q(w))                        # :63
 
     # ---- VBLinear.lua:77-88 -------------------------------------------------
     def compute_prior(self):
@@ -192,42 +208,51 @@ class VBLinearOracle:
         return (LCfirst + LCsecond) * (1.0 / opt["B"])                                     # :102
 
     def clamp_to_map(self):
-        self.weight.copy_(self.means)                       # :106
+        self.weight.copy_(self.q(self.means))               # :106
 
     # ---- inherited nn.Linear (un-vendored) ----------------------------------
     def updateOutput(self, input: torch.Tensor, zeta: Optional[torch.Tensor] = None):
+        q = self.q
+        input = q(input)
         self.input = input
-        if self.lrt and not getattr(self, "_map", False):
+        if self.lrt and getattr(self, "_map", False):
+            self.output = input @ q(self.means).t() + self.bias
+            return self.output
+        if self.lrt:
             # A12 forward: M = X mu^T + b, V = X^2 (s2)^T, Y = M + sqrt(V) zeta
-            s2 = torch.exp(self.lvars)
-            M = input @ self.means.t() + self.bias
-            V = (input * input) @ s2.t()
+            s2 = q(torch.exp(self.lvars))
+            M = input @ q(self.means).t() + self.bias
+            V = q(input * input) @ s2.t()
             if zeta is None:
                 zeta = torch.from_numpy(self.rng.normal(0.0, 1.0, tuple(M.shape)))
             self.zeta = zeta.to(self.dtype)
             sq = torch.sqrt(V)
-            self._R = self.zeta / (2.0 * sq)
+            self._R = q(self.zeta / (2.0 * sq))
             self.output = M + sq * self.zeta
             return self.output
         self.output = input @ self.weight.t() + self.bias   # nn.Linear:updateOutput
         return self.output
 
     def updateGradInput(self, input, gradOutput):
+        q = self.q
+        input, gradOutput = q(input), q(gradOutput)
         if self.lrt and not getattr(self, "_map", False):
-            s2 = torch.exp(self.lvars)
-            H = gradOutput * self._R
-            self.gradInput = gradOutput @ self.means + 2.0 * input * (H @ s2)
+            s2 = q(torch.exp(self.lvars))
+            H = q(gradOutput * self._R)
+            self.gradInput = gradOutput @ q(self.means) + 2.0 * input * (H @ s2)
             return self.gradInput
         self.gradInput = gradOutput @ self.weight           # nn.Linear:updateGradInput
         return self.gradInput
 
     # ---- VBLinear.lua:112-118 -----------------------------------------------
     def accGradParameters(self, input, gradOutput, scale=1.0):
+        q = self.q
+        input, gradOutput = q(input), q(gradOutput)
         if self.lrt and not getattr(self, "_map", False):
-            H = gradOutput * self._R
+            H = q(gradOutput * self._R)
             self.gradWeight.add_(scale * (gradOutput.t() @ input))
             self.gradBias.add_(scale * gradOutput.sum(0))
-            self.gradSum.add_(H.t() @ (input * input))
+            self.gradSum.add_(H.t() @ q(input * input))
             return
         self.gradWeight.add_(scale * (gradOutput.t() @ input))   # :113 parent
         self.gradBias.add_(scale * gradOutput.sum(0))            # :113 parent
@@ -286,8 +311,9 @@ class VBLinearOracle:
 class LinearOracle:
     """Plain nn.Linear (mlp.lua:29 output layer; quirk Q8)."""
 
-    def __init__(self, inputSize, outputSize, dtype=torch.float64, rng=None):
+    def __init__(self, inputSize, outputSize, dtype=torch.float64, rng=None, operand_round=None):
         rng = rng or np.random.RandomState(3)
+        self.q = operand_round or _ident
         stdv = 1.0 / math.sqrt(inputSize)
         self.weight = torch.from_numpy(rng.uniform(-stdv, stdv, (outputSize, inputSize))).to(dtype)
         self.bias = torch.from_numpy(rng.uniform(-stdv, stdv, (outputSize,))).to(dtype)
@@ -295,14 +321,15 @@ class LinearOracle:
         self.gradBias = torch.zeros_like(self.bias)
 
     def updateOutput(self, input):
-        self.output = input @ self.weight.t() + self.bias
+        self.output = self.q(input) @ self.q(self.weight).t() + self.bias
         return self.output
 
     def updateGradInput(self, input, gradOutput):
-        self.gradInput = gradOutput @ self.weight
+        self.gradInput = self.q(gradOutput) @ self.q(self.weight)
         return self.gradInput
 
     def accGradParameters(self, input, gradOutput, scale=1.0):
+        input, gradOutput = self.q(input), self.q(gradOutput)
         self.gradWeight.add_(scale * (gradOutput.t() @ input))
         self.gradBias.add_(scale * gradOutput.sum(0))
 
@@ -344,24 +371,25 @@ def get_accuracy(outputs, targets1):    # utils.lua:11-27 (percent)
 class MLPOracle:
     """mlp.lua:7-142.  Reshape -> [VBLinear -> ReLU] x H -> Linear -> LogSoftMax."""
 
-    def __init__(self, opt: dict, dtype=torch.float64, seed: int = 3):
-        self.buildModel(opt, dtype, seed)
+    def __init__(self, opt: dict, dtype=torch.float64, seed: int = 3, operand_round=None):
+        self.buildModel(opt, dtype, seed, operand_round)
 
-    def buildModel(self, opt, dtype=torch.float64, seed=3):      # mlp.lua:7-60
+    def buildModel(self, opt, dtype=torch.float64, seed=3, operand_round=None):      # mlp.lua:7-60
         self.opt = opt
         self.dtype = dtype
+        self.q = operand_round or _ident
         rng = np.random.RandomState(seed)
         self.rng = rng
         sizes = [opt["input_size"]] + list(opt["hidden"])
         self.vb: List[VBLinearOracle] = []
         for i in range(1, len(sizes)):                            # :13-28
-            self.vb.append(VBLinearOracle(sizes[i - 1], sizes[i], opt, dtype, rng))
+            self.vb.append(VBLinearOracle(sizes[i - 1], sizes[i], opt, dtype, rng, operand_round))
         C = len(opt["classes"])
         if opt.get("vb_output"):                                  # convnet.lua:30 (Q8)
-            self.out = VBLinearOracle(sizes[-1], C, opt, dtype, rng)
+            self.out = VBLinearOracle(sizes[-1], C, opt, dtype, rng, operand_round)
             self.vb_all = self.vb + [self.out]
         else:
-            self.out = LinearOracle(sizes[-1], C, dtype, rng)     # :29
+            self.out = LinearOracle(sizes[-1], C, dtype, rng, operand_round)     # :29
             self.vb_all = list(self.vb)
         # mlp.lua:47-55: re-init every Linear's *weight* ~ N(0, sqrt(2/fan_in)), bias = 0.
         # For VB layers this touches .weight (overwritten by the next sample()), not .means.
@@ -387,12 +415,13 @@ class MLPOracle:
             lyr.sample(None if eps_list is None else eps_list[k])
 
     def run(self, inputs, targets, zeta_list=None, backward=True):        # mlp.lua:76-84
-        x = inputs.reshape(inputs.shape[0], -1).to(self.dtype)            # nn.Reshape (:12)
+        q = self.q
+        x = q(inputs.reshape(inputs.shape[0], -1).to(self.dtype))         # nn.Reshape (:12)
         acts = [x]
         for k, lyr in enumerate(self.vb):
             z = None if zeta_list is None else zeta_list[k]
             y = lyr.updateOutput(acts[-1], z) if lyr.lrt else lyr.updateOutput(acts[-1])
-            acts.append(torch.clamp(y, min=0))                            # nn.ReLU (:19,27)
+            acts.append(q(torch.clamp(y, min=0)))                         # nn.ReLU (:19,27)
         if isinstance(self.out, VBLinearOracle) and self.out.lrt:
             z = None if zeta_list is None else zeta_list[len(self.vb)]
             logits = self.out.updateOutput(acts[-1], z)
@@ -402,11 +431,11 @@ class MLPOracle:
         self.outputs = logp
         if backward:
             df_do = class_nll_backward(logp, targets)                     # :78
-            g = log_softmax_backward(logp, df_do)                         # :79 model:backward
+            g = q(log_softmax_backward(logp, df_do))                      # :79 model:backward
             g_in = self.out.updateGradInput(acts[-1], g)
             self.out.accGradParameters(acts[-1], g, 1.0)
             for k in range(len(self.vb) - 1, -1, -1):
-                g = g_in * (acts[k + 1] > 0).to(self.dtype)               # ReLU backward
+                g = q(g_in * (acts[k + 1] > 0).to(self.dtype))            # ReLU backward
                 g_in = self.vb[k].updateGradInput(acts[k], g)             # computed even for k=0
                 self.vb[k].accGradParameters(acts[k], g, 1.0)
         error = class_nll_forward(logp, targets)                          # :80

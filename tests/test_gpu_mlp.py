@@ -2,9 +2,14 @@
 
 The fused minibatch draws its noise on the device (Philox); the tests dump exactly that noise
 through vbnn_layer_draw_noise and inject it into the CPU oracle, so both sides see identical
-epsilon / zeta.  Tolerances (relative Frobenius error per tensor): fp32 mode <= 2e-4 after
-optimiser steps (<= 1e-5 on accumulators); bf16-operand mode <= 3e-2 on accumulators and
-<= 1e-2 on parameters."""
+epsilon / zeta.  Tolerances (relative Frobenius error per tensor):
+  * fp32 mode vs the fp64 oracle: <= 1e-5 on accumulators, <= 2e-4 after optimiser steps;
+  * bf16-operand mode vs the oracle restating the same bf16 operand rounding
+    (operand_round=round_bf16, accumulation in fp64): <= 5e-3 -- the residual is one-ulp bf16
+    rounding flips where the fp32 and fp64 pre-rounding values straddle a tie;
+  * bf16-operand mode vs the un-rounded fp64 oracle: <= 0.12, stated separately -- this is the
+    inherent cost of bf16 operands through three layers (measured 2.5-6 % on first-layer
+    gradients, identical in a pure-torch emulation; see tools/diag_bf16.py)."""
 import math
 import os
 
@@ -28,7 +33,8 @@ def cpu(t):
     return t.detach().float().cpu().numpy()
 
 
-def build_pair(ctx, sizes, N, S, B, precision, reparam, seed=0, strict=True, vb_output=False, lr_mu=None):
+def build_pair(ctx, sizes, N, S, B, precision, reparam, seed=0, strict=True, vb_output=False, lr_mu=None,
+               operand_round=None, dtype=torch.float64):
     import vbnn_b200
     from vbnn_b200 import _lib as L
     over = dict(input_size=sizes[0], hidden=list(sizes[1:-1]), classes=[str(i) for i in range(sizes[-1])],
@@ -39,7 +45,7 @@ def build_pair(ctx, sizes, N, S, B, precision, reparam, seed=0, strict=True, vb_
     gopt = vbnn_b200.default_opt(precision=precision, **over)
     net = vbnn_b200.MLP(gopt, ctx, max_batch=N)
     oopt = O.default_opt(**over)
-    ref = O.MLPOracle(oopt, torch.float64, seed=3)
+    ref = O.MLPOracle(oopt, dtype, seed=3, operand_round=operand_round)
     rng = np.random.RandomState(seed)
     layers = ref.vb + [ref.out]
     for k, (gl, ol) in enumerate(zip(net.model, layers)):
@@ -111,10 +117,13 @@ def test_fused_step_vs_oracle(ctx, precision, reparam, vb_output):
     """vbnn_mlp_step (S samples batched per launch; CUDA graph from the 2nd minibatch on) against
     the oracle fed with the device-drawn noise."""
     sizes, N, S = [40, 48, 36, 6], 24, 3
-    net, ref, gopt, oopt = build_pair(ctx, sizes, N, S, 30.0, precision, reparam, vb_output=vb_output)
+    bf = precision == "bf16"
+    net, ref, gopt, oopt = build_pair(ctx, sizes, N, S, 30.0, precision, reparam, vb_output=vb_output,
+                                      operand_round=O.round_bf16 if bf else None)
+    ref64 = build_pair(ctx, sizes, N, S, 30.0, precision, reparam, vb_output=vb_output)[1] if bf else None
     rng = np.random.RandomState(5)
-    tol_acc = 1e-5 if precision == "fp32" else 3e-2
-    tol_par = 2e-4 if precision == "fp32" else 1e-2
+    tol_acc = 5e-3 if bf else 1e-5
+    tol_par = 5e-3 if bf else 2e-4
     nvb = len(ref.vb_all)
     gidx = lambda k: k if k < len(ref.vb) else len(net.model) - 1
     for it in range(4):
@@ -123,13 +132,11 @@ def test_fused_step_vs_oracle(ctx, precision, reparam, vb_output):
         noise = [[torch.from_numpy(cpu(net.model[gidx(k)].draw_noise(step, s, rows=N)).astype(np.float64))
                   for k in range(nvb)] for s in range(S)]
         err, acc = net.train_step(torch.from_numpy(Xn).float().cuda(), torch.from_numpy(Tn).float().cuda())
-        if reparam == "local":
-            rerr, racc, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), zeta=noise)
-        else:
-            rerr, racc, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), eps=noise)
+        kw = dict(zeta=noise) if reparam == "local" else dict(eps=noise)
+        rerr, racc, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), **kw)
         assert ctx.get_step() == step + 1
-        assert abs(err - rerr) < (1e-4 if precision == "fp32" else 3e-2) * abs(rerr), (it, err, rerr)
-        if precision == "fp32":
+        assert abs(err - rerr) < (2e-3 if bf else 1e-4) * abs(rerr), (it, err, rerr)
+        if not bf:
             assert abs(acc - racc) < 1e-3
         for k, ol in enumerate(ref.vb_all):
             gl = net.model[gidx(k)]
@@ -142,6 +149,12 @@ def test_fused_step_vs_oracle(ctx, precision, reparam, vb_output):
             assert rel(cpu(gl.bias), ol.bias.numpy()) < max(tol_par, 1e-4), (it, k, "bias")
         if not vb_output:
             assert rel(cpu(net.model[-1].weight), ref.out.weight.numpy()) < tol_par
+        if bf and it == 0:
+            # the bf16-vs-fp64 gap, stated separately (inherent to bf16 operands)
+            e64, _, accs64 = oracle_step(ref64, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), **kw)
+            assert abs(err - e64) < 2e-2 * abs(e64)
+            for k in range(nvb):
+                assert rel(cpu(net.model[gidx(k)].gradWeight), accs64[k][0].numpy()) < 0.12, (k, "gW vs fp64")
 
 
 def test_graph_replay_equals_eager(ctx):
@@ -223,26 +236,42 @@ def test_c1_config_learns(ctx):
 
 @pytest.mark.parametrize("sizes,N,S,reparam", [([784, 1200, 1200, 10], 1024, 10, "weight"),
                                               ([1024, 1024, 1024, 1000], 2048, 1, "local")])
-def test_full_size_bf16_tensor_core_path_matches_fp32_path(ctx, sizes, N, S, reparam):
-    """BASELINE-size minibatch (C2; a C3-shaped net): the tcgen05 path and the fp32 CUDA-core path
-    (itself oracle-checked above) draw identical Philox noise, so their accumulators must agree
-    to bf16-operand accuracy."""
+def test_full_size_bf16_tensor_core_path(ctx, sizes, N, S, reparam):
+    """BASELINE-size minibatch (C2 exactly; a C3-shaped net) on the tcgen05 path, checked two ways:
+    (1) against the oracle restating the bf16 operand rounding, fed the device-drawn noise
+    (fp32 accumulate on the CPU to keep it to seconds): <= 5e-3;
+    (2) against this library's own fp32 CUDA-core path (oracle-checked above) with identical Philox
+    noise: the inherent bf16-operand gap, <= 0.12 on gradients and <= 2e-2 on the loss."""
     rng = np.random.RandomState(3)
-    X = torch.from_numpy(rng.randn(N, sizes[0])).float().cuda()
-    T = torch.from_numpy(rng.randint(1, sizes[-1] + 1, N).astype(np.float32)).cuda()
+    Xn = rng.randn(N, sizes[0]).astype(np.float32)
+    Tn = rng.randint(1, sizes[-1] + 1, N).astype(np.float32)
+    X, T = torch.from_numpy(Xn).cuda(), torch.from_numpy(Tn).cuda()
     out = {}
     for precision in ("fp32", "bf16"):
         ctx.set_step(11)
-        net, _, _, _ = build_pair(ctx, sizes, N, S, 58.6, precision, reparam, seed=6, strict=False)
+        bf = precision == "bf16"
+        net, ref, _, oopt = build_pair(ctx, sizes, N, S, 58.6, precision, reparam, seed=6, strict=False,
+                                       operand_round=O.round_bf16 if bf else None, dtype=torch.float32)
+        if bf:
+            nvb = len(ref.vb)
+            noise = [[net.model[k].draw_noise(11, s, rows=N).cpu() for k in range(nvb)] for s in range(S)]
         err, acc = net.train_step(X, T)
         assert math.isfinite(err)
         out[precision] = (err, [cpu(m.gradWeight).copy() for m in net.model],
                           [cpu(m.gradSum).copy() for m in net.model[:-1]], [cpu(m.means).copy() for m in net.model[:-1]])
+        if bf:
+            kw = dict(zeta=noise) if reparam == "local" else dict(eps=noise)
+            rerr, _, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), **kw)
+            assert abs(err - rerr) < 2e-3 * abs(rerr)
+            for k in range(nvb):
+                assert rel(out["bf16"][1][k], accs[k][0].numpy()) < 5e-3, (k, "gW vs bf16 oracle")
+                assert rel(out["bf16"][2][k], accs[k][1].numpy()) < 1e-2, (k, "gS vs bf16 oracle")
+                assert rel(out["bf16"][3][k], ref.vb[k].means.numpy()) < 5e-3, (k, "means vs bf16 oracle")
         del net
     assert abs(out["bf16"][0] - out["fp32"][0]) < 2e-2 * abs(out["fp32"][0])
     for a, b in zip(out["bf16"][1], out["fp32"][1]):
-        assert rel(a, b) < 3e-2
+        assert rel(a, b) < 0.12
     for a, b in zip(out["bf16"][2], out["fp32"][2]):
-        assert rel(a, b) < 5e-2
+        assert rel(a, b) < 0.15
     for a, b in zip(out["bf16"][3], out["fp32"][3]):
-        assert rel(a, b) < 1e-2
+        assert rel(a, b) < 2e-2

@@ -48,6 +48,8 @@ _PROTOS = {
     "vbnn_ctx_create": (C.c_int, [C.c_int, _P, C.c_uint64, C.POINTER(_P)]),
     "vbnn_ctx_destroy": (C.c_int, [_P]),
     "vbnn_ctx_synchronize": (C.c_int, [_P]),
+    "vbnn_ctx_profile": (C.c_int, [_P, C.c_int]),
+    "vbnn_ctx_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
     "vbnn_ctx_set_step": (C.c_int, [_P, C.c_uint32]),
     "vbnn_ctx_get_step": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "vbnn_layer_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(VbnnOpts), C.POINTER(_P)]),

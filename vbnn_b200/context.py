@@ -36,6 +36,20 @@ class Context:
         L.check(L.lib().vbnn_ctx_get_step(self.handle, C.byref(v)))
         return int(v.value)
 
+    def profile(self, enable: bool):
+        L.check(L.lib().vbnn_ctx_profile(self.handle, 1 if enable else 0))
+
+    def profile_read(self):
+        """{class: (total_ms, launches, flops)} of the tensor-core GEMM launches since profile(True)."""
+        names = ["store", "fwd", "fwd_lrt", "dx", "dx_lrt", "dw", "dw_lrt"]
+        out = {}
+        for cls, name in enumerate(names):
+            ms, n, fl = C.c_double(), C.c_longlong(), C.c_double()
+            L.check(L.lib().vbnn_ctx_profile_read(self.handle, cls, C.byref(ms), C.byref(n), C.byref(fl)))
+            if n.value:
+                out[name] = (ms.value, n.value, fl.value)
+        return out
+
     def close(self):
         if self.handle:
             L.lib().vbnn_ctx_destroy(self.handle)

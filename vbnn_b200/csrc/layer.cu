@@ -79,14 +79,15 @@ int layer_compute_prior_internal(vbnn_layer* L) {
 }
 
 int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts* opts, int S_alloc,
-                          float* gW, float* gS, float* gb, vbnn_layer** out) {
+                          float* gW, float* gS, float* gb, int id, vbnn_layer** out) {
   VB_CHECK(ctx && out && opts, VBNN_E_INVALID, "layer_create: null argument");
   VB_CHECK(I > 0 && O > 0, VBNN_E_INVALID, "layer_create: bad sizes %d x %d", O, I);
   VB_CHECK(kind == VBNN_KIND_VB || kind == VBNN_KIND_LINEAR, VBNN_E_INVALID, "layer_create: bad kind");
   VB_CUDA(cudaSetDevice(ctx->device));
   vbnn_layer* L = new vbnn_layer();
   L->ctx = ctx; L->I = I; L->O = O; L->kind = kind; L->opts = *opts;
-  L->id = ctx->next_layer_id++;
+  // Philox stream id: position inside an mlp (identical on every rank / rebuild) or a ctx counter
+  L->id = id >= 0 ? id : 0x1000 + ctx->next_layer_id++;
   L->ldI = round_up(I, 8); L->ldO = round_up(O, 8);
   L->S_alloc = S_alloc < 1 ? 1 : S_alloc;
   cudaStream_t st = ctx->stream;
@@ -248,6 +249,39 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
   return VBNN_OK;
 }
 
+int tc_gemm(vbnn_ctx* c, int mode, const TcGemmArgs& g, const EpiParams& p) {
+  if (!c->profiling) return gemm_tc_launch(mode, g, p, c->stream, &c->launches);
+  auto get_event = [&](cudaEvent_t* e) -> int {
+    if (!c->prof_pool.empty()) { *e = c->prof_pool.back(); c->prof_pool.pop_back(); return VBNN_OK; }
+    VB_CUDA(cudaEventCreate(e));
+    return VBNN_OK;
+  };
+  vbnn_ctx::ProfRec r;
+  VB_TRY(get_event(&r.a));
+  VB_TRY(get_event(&r.b));
+  r.cls = mode;
+  r.flops = 2.0 * g.M * (double)g.N * g.K * g.batch * (epi_is_dual(mode) ? 2.0 : 1.0);
+  VB_CUDA(cudaEventRecord(r.a, c->stream));
+  int rc = gemm_tc_launch(mode, g, p, c->stream, &c->launches);
+  VB_CUDA(cudaEventRecord(r.b, c->stream));
+  c->prof_recs.push_back(r);
+  if (c->prof_recs.size() >= 4096) VB_TRY(prof_collect(c));
+  return rc;
+}
+
+int prof_collect(vbnn_ctx* c) {
+  if (c->prof_recs.empty()) return VBNN_OK;
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& r : c->prof_recs) {
+    float ms = 0.f;
+    VB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
+    c->prof_ms[r.cls & 7] += ms; c->prof_flops[r.cls & 7] += r.flops; c->prof_n[r.cls & 7] += 1;
+    c->prof_pool.push_back(r.a); c->prof_pool.push_back(r.b);
+  }
+  c->prof_recs.clear();
+  return VBNN_OK;
+}
+
 }  // namespace vbnn
 
 using namespace vbnn;
@@ -306,6 +340,8 @@ extern "C" int vbnn_ctx_destroy(vbnn_ctx* c) {
   if (!c) return VBNN_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  prof_collect(c);
+  for (cudaEvent_t e : c->prof_pool) cudaEventDestroy(e);
   vbnn_comm_destroy(c);
   DEV_FREE(c->d_step); DEV_FREE(c->d_partials);
   if (c->h_partials) cudaFreeHost(c->h_partials);
@@ -319,6 +355,21 @@ extern "C" int vbnn_ctx_destroy(vbnn_ctx* c) {
 extern "C" int vbnn_ctx_synchronize(vbnn_ctx* c) {
   VB_CHECK(c, VBNN_E_INVALID, "null ctx");
   VB_CUDA(cudaStreamSynchronize(c->stream));
+  return VBNN_OK;
+}
+extern "C" int vbnn_ctx_profile(vbnn_ctx* c, int enable) {
+  VB_CHECK(c, VBNN_E_INVALID, "null ctx");
+  VB_TRY(prof_collect(c));
+  c->profiling = enable != 0;
+  if (enable) for (int i = 0; i < 8; ++i) { c->prof_ms[i] = 0; c->prof_flops[i] = 0; c->prof_n[i] = 0; }
+  return VBNN_OK;
+}
+extern "C" int vbnn_ctx_profile_read(vbnn_ctx* c, int cls, double* total_ms, long long* launches, double* flops) {
+  VB_CHECK(c && cls >= 0 && cls < 8, VBNN_E_INVALID, "vbnn_ctx_profile_read: bad argument");
+  VB_TRY(prof_collect(c));
+  if (total_ms) *total_ms = c->prof_ms[cls];
+  if (launches) *launches = c->prof_n[cls];
+  if (flops) *flops = c->prof_flops[cls];
   return VBNN_OK;
 }
 extern "C" int vbnn_ctx_set_step(vbnn_ctx* c, uint32_t step) {
@@ -337,7 +388,7 @@ extern "C" int vbnn_ctx_get_step(vbnn_ctx* c, uint32_t* step) {
 // ============================================================ layer ========================
 extern "C" int vbnn_layer_create(vbnn_ctx* ctx, int inputSize, int outputSize, int kind,
                                  const vbnn_opts* opts, vbnn_layer** out) {
-  return layer_create_internal(ctx, inputSize, outputSize, kind, opts, 1, nullptr, nullptr, nullptr, out);
+  return layer_create_internal(ctx, inputSize, outputSize, kind, opts, 1, nullptr, nullptr, nullptr, -1, out);
 }
 
 extern "C" int vbnn_layer_destroy(vbnn_layer* L) {
@@ -430,7 +481,7 @@ extern "C" int vbnn_layer_forward(vbnn_layer* L, const float* X, int N, float* Y
     const bf16* w = L->kind == VBNN_KIND_LINEAR ? L->w_bf16 : (is_lrt(L) ? L->mu_bf16 : L->w_bf16);
     g.B1 = {w, L->ldI, 1, 0};
     if (lrt) { g.A2 = {(const bf16*)L->xs2, L->ldI, 1, 0}; g.B2 = {L->s2_bf16, L->ldI, 1, 0}; }
-    return gemm_tc_launch(mode, g, p, st, &L->ctx->launches);
+    return tc_gemm(L->ctx, mode, g, p);
   }
   SimtGemmArgs g;
   memset(&g, 0, sizeof(g));
@@ -481,7 +532,7 @@ extern "C" int vbnn_layer_backward_data(vbnn_layer* L, const float* X, const flo
     const bf16* w = L->kind == VBNN_KIND_LINEAR ? L->w_bf16 : (is_lrt(L) ? L->mu_bf16 : L->w_bf16);
     g.B1 = {w, L->ldI, 0, 0};
     if (lrt) { g.A2 = {(const bf16*)L->hs, L->ldO, 1, 0}; g.B2 = {L->s2_bf16, L->ldI, 0, 0}; }
-    return gemm_tc_launch(mode, g, p, st, &L->ctx->launches);
+    return tc_gemm(L->ctx, mode, g, p);
   }
   if (lrt) { p.xprev = X; p.ld_x = L->I; }
   SimtGemmArgs g;
@@ -519,7 +570,7 @@ extern "C" int vbnn_layer_acc_grad(vbnn_layer* L, const float* X, const float* G
     g.A1 = {(const bf16*)L->gs_, L->ldO, 0, 0};
     g.B1 = {(const bf16*)L->xs, L->ldI, 0, 0};
     if (lrt) { g.A2 = {(const bf16*)L->hs, L->ldO, 0, 0}; g.B2 = {(const bf16*)L->xs2, L->ldI, 0, 0}; }
-    VB_TRY(gemm_tc_launch(mode, g, p, st, &L->ctx->launches));
+    VB_TRY(tc_gemm(L->ctx, mode, g, p));
   } else {
     SimtGemmArgs g;
     memset(&g, 0, sizeof(g));
@@ -739,5 +790,5 @@ extern "C" int vbnn_gemm_bf16(vbnn_ctx* ctx, const uint16_t* A, int lda, int a_k
   EpiParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.out_f32 = D; p.ld_f32 = ldd; p.zs_f32 = strideD;
-  return gemm_tc_launch(EPI_STORE, g, p, ctx->stream, &ctx->launches);
+  return tc_gemm(ctx, EPI_STORE, g, p);
 }

@@ -114,7 +114,7 @@ int forward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, bool map_mod
       g.A2 = {(const bf16*)m->act2[j], ldi, 1, zs_in};
       g.B2 = {L->s2_bf16, L->ldI, 1, 0};
     }
-    return gemm_tc_launch(mode, g, p, st, &m->ctx->launches);
+    return tc_gemm(m->ctx, mode, g, p);
   }
   SimtGemmArgs g;
   memset(&g, 0, sizeof(g));
@@ -186,7 +186,7 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
         g.A2 = {(const bf16*)m->H[j], ldo, 1, zs_out};
         g.B2 = {L->s2_bf16, L->ldI, 0, 0};
       }
-      VB_TRY(gemm_tc_launch(mode, g, p, st, &m->ctx->launches));
+      VB_TRY(tc_gemm(m->ctx, mode, g, p));
     } else {
       SimtGemmArgs g;
       memset(&g, 0, sizeof(g));
@@ -221,7 +221,7 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
         g.A2 = {(const bf16*)m->H[j], ldo, 0, zs_out};
         g.B2 = {(const bf16*)m->act2[j], ldi, 0, zs_in};
       }
-      VB_TRY(gemm_tc_launch(mode, g, p, st, &m->ctx->launches));
+      VB_TRY(tc_gemm(m->ctx, mode, g, p));
     } else {
       SimtGemmArgs g;
       memset(&g, 0, sizeof(g));
@@ -277,7 +277,7 @@ int step_body(vbnn_mlp* m, int N) {
 int step_enqueue(vbnn_mlp* m, int N) {
   vbnn_ctx* c = m->ctx;
   cudaStream_t st = c->stream;
-  const bool graphable = m->use_graph && c->nranks == 1;
+  const bool graphable = m->use_graph && c->nranks == 1 && !c->profiling;
   if (!graphable || m->eager_steps < 1) {
     m->eager_steps++;
     return step_body(m, N);
@@ -347,7 +347,7 @@ extern "C" int vbnn_mlp_create(vbnn_ctx* ctx, const int* sizes, int n_sizes, int
     vbnn_layer* L = nullptr;
     r = layer_create_internal(ctx, sizes[j], sizes[j + 1], vb ? VBNN_KIND_VB : VBNN_KIND_LINEAR, opts,
                               (vb && !m->lrt) ? m->Z : 1, m->grad_arena + off_gW[j],
-                              vb ? m->grad_arena + off_gS[j] : nullptr, m->grad_arena + off_gb[j], &L);
+                              vb ? m->grad_arena + off_gS[j] : nullptr, m->grad_arena + off_gb[j], j, &L);
     if (r == VBNN_OK) { L->owned_by_mlp = true; m->layers.push_back(L); }
   }
   // ---- activations ----

@@ -18,6 +18,12 @@ struct vbnn_ctx {
   float* h_scalars = nullptr;        // pinned scratch for scalar read-backs
   int next_layer_id = 0;
   long long launches = 0;
+  // per-launch device timing of the tensor-core GEMM (bench.py roofline)
+  bool profiling = false;
+  struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  double prof_ms[8] = {0}; double prof_flops[8] = {0}; long long prof_n[8] = {0};
   // data parallel
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
@@ -83,10 +89,13 @@ struct vbnn_mlp {
 
 namespace vbnn {
 int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts* opts, int S_alloc,
-                          float* gW, float* gS, float* gb, vbnn_layer** out);
+                          float* gW, float* gS, float* gb, int id, vbnn_layer** out);
 int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t);
 int layer_refresh_copies(vbnn_layer* L);
 int layer_compute_prior_internal(vbnn_layer* L);
 PhiloxStream layer_stream(const vbnn_layer* L, uint32_t kind, int sample);
 int comm_allreduce_internal(vbnn_ctx* ctx, float* buf, size_t count, cudaStream_t st);
+// tensor-core GEMM launch with optional event bracketing (ctx->profiling)
+int tc_gemm(vbnn_ctx* ctx, int mode, const TcGemmArgs& g, const EpiParams& p);
+int prof_collect(vbnn_ctx* ctx);
 }  // namespace vbnn
