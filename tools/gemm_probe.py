@@ -50,20 +50,20 @@ if bad.any():
 def main():
     cases = []
     for ak, bk in [(1, 1), (1, 0), (0, 1), (0, 0)]:
-        for (M, N, K) in [(128, 128, 16), (128, 128, 64), (128, 128, 128), (128, 256, 64), (256, 256, 256)]:
-            for bn in (128, 256):
+        for (M, N, K) in [(128, 128, 16), (128, 256, 64), (256, 256, 256), (300, 520, 200)]:
+            for bn, cg in ((128, 1), (256, 1), (256, 2)):
                 if N < bn and bn == 256:
                     continue
-                cases.append(dict(ak=ak, bk=bk, M=M, N=N, K=K, bn=bn))
+                cases.append(dict(ak=ak, bk=bk, M=M, N=N, K=K, bn=bn, cg=cg))
     for c in cases:
-        env = dict(os.environ, VBNN_TC_BN=str(c["bn"]))
+        env = dict(os.environ, VBNN_TC_BN=str(c["bn"]), VBNN_TC_CG=str(c["cg"]))
         src = CASE % dict(c, root=ROOT)
         try:
             p = subprocess.run([sys.executable, "-c", src], capture_output=True, text=True, timeout=120, env=env)
             out = (p.stdout + p.stderr[-600:]).strip()
         except subprocess.TimeoutExpired:
             out = "TIMEOUT"
-        print(f"--- ak={c['ak']} bk={c['bk']} M={c['M']} N={c['N']} K={c['K']} bn={c['bn']}\n{out}", flush=True)
+        print(f"--- ak={c['ak']} bk={c['bk']} M={c['M']} N={c['N']} K={c['K']} bn={c['bn']} cg={c['cg']}\n{out}", flush=True)
 
 
 if __name__ == "__main__":

@@ -104,9 +104,29 @@ __device__ __forceinline__ void store4(T* p, const float (&v)[4], int nvalid, bo
   }
 }
 
+// Philox stream of this launch with the device-side step counter resolved ONCE per thread (the
+// kernels call this at entry; doing it per quad put a dependent global load in front of every
+// Philox chain).
+__device__ __forceinline__ PhiloxStream epi_stream(const EpiParams& p) {
+  PhiloxStream ps = p.ps;
+  if (p.step_ptr) ps.step = *p.step_ptr;
+  return ps;
+}
+
+__device__ __forceinline__ void load_bias4(const float* bias, int col, int nvalid, float (&b)[4]) {
+  if (bias == nullptr) { b[0] = b[1] = b[2] = b[3] = 0.f; return; }
+  if (nvalid == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(bias + col));   // col % 4 == 0, cudaMalloc-aligned
+    b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = j < nvalid ? __ldg(bias + col + j) : 0.f;
+  }
+}
+
 // Process one quad.  a1/a2: accumulator values (a2 only for dual modes).
 template <int MODE, typename AT>
-__device__ __forceinline__ void epi_quad(const EpiParams& p, int z, int row, int col,
+__device__ __forceinline__ void epi_quad(const EpiParams& p, const PhiloxStream& ps0, int z, int row, int col,
                                          const float (&a1)[4], const float (&a2)[4]) {
   if (row >= p.M || col >= p.N) return;
   const int nvalid = min(4, p.N - col);
@@ -116,11 +136,11 @@ __device__ __forceinline__ void epi_quad(const EpiParams& p, int z, int row, int
   if constexpr (MODE == EPI_STORE) {
     store4<float>(p.out_f32 + z * p.zs_f32 + (long long)row * p.ld_f32 + col, a1, nvalid, vec_f32);
   } else if constexpr (MODE == EPI_FWD) {
-    float y[4];
+    float y[4], b[4];
+    load_bias4(p.bias, col, nvalid, b);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float b = (p.bias != nullptr && j < nvalid) ? __ldg(p.bias + col + j) : 0.f;
-      y[j] = a1[j] + b;
+      y[j] = a1[j] + b[j];
       if (p.relu) y[j] = fmaxf(y[j], 0.f);
     }
     if (p.out_f32)
@@ -132,20 +152,21 @@ __device__ __forceinline__ void epi_quad(const EpiParams& p, int z, int row, int
     if (p.noise) {
       load4<float>(p.noise + z * p.zs_noise + (long long)row * p.N + col, zt, nvalid, (p.N & 3) == 0);
     } else {
-      PhiloxStream ps = p.ps;
+      PhiloxStream ps = ps0;
       ps.sample += (uint32_t)z;
-      if (p.step_ptr) ps.step = *p.step_ptr;
       uint32_t q = (uint32_t)((p.N + 3) >> 2);
       philox_normal4(ps, (uint32_t)(row + p.row0) * q + (uint32_t)(col >> 2), zt);
     }
-    float y[4], y2[4], r[4];
+    float y[4], y2[4], r[4], b[4];
+    load_bias4(p.bias, col, nvalid, b);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float b = (p.bias != nullptr && j < nvalid) ? __ldg(p.bias + col + j) : 0.f;
-      float v = fmaxf(a2[j], 0.f);
-      float sq = sqrtf(v);
-      y[j] = a1[j] + b + sq * zt[j];
-      r[j] = sq > 0.f ? zt[j] / (2.f * sq) : 0.f;
+      // sqrt(V) and zeta / (2 sqrt(V)) from one MUFU.RSQ (V = 0 only for an all-zero input row)
+      const float v = a2[j];
+      const float rs = v > 0.f ? rsqrtf(v) : 0.f;
+      const float sq = v * rs;
+      y[j] = a1[j] + b[j] + sq * zt[j];
+      r[j] = 0.5f * zt[j] * rs;
     }
     if (p.out_f32)
       store4<float>(p.out_f32 + z * p.zs_f32 + (long long)row * p.ld_f32 + col, y, nvalid, vec_f32);
@@ -200,9 +221,8 @@ __device__ __forceinline__ void epi_quad(const EpiParams& p, int z, int row, int
         if (p.noise) {
           load4<float>(p.noise + z * p.zs_noise + (long long)row * p.N + col, e, nvalid, (p.N & 3) == 0);
         } else {
-          PhiloxStream ps = p.ps;
+          PhiloxStream ps = ps0;
           ps.sample += (uint32_t)z;
-          if (p.step_ptr) ps.step = *p.step_ptr;
           uint32_t q = (uint32_t)((p.N + 3) >> 2);
           philox_normal4(ps, (uint32_t)row * q + (uint32_t)(col >> 2), e);
         }

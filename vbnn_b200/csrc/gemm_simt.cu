@@ -85,8 +85,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtGemmArgs g, EpiParam
     }
     __syncthreads();
   }
+  const PhiloxStream ps = epi_stream(p);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) epi_quad<MODE, float>(p, z, m0 + ty * 4 + i, n0 + tx * 4, acc1[i], acc2[i]);
+  for (int i = 0; i < 4; ++i) epi_quad<MODE, float>(p, ps, z, m0 + ty * 4 + i, n0 + tx * 4, acc1[i], acc2[i]);
 }
 
 template <int MODE>

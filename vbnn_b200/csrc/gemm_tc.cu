@@ -20,6 +20,7 @@
 
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace vbnn {
 
@@ -36,6 +37,15 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // minus barriers + alignment s
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -45,6 +55,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(cta)
+      : "memory");
 }
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t done;
@@ -72,26 +91,44 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// CG == 2: both CTAs of the pair load into their own smem but complete the transaction on the
+// LEADER's barrier (the CTA-rank bit of the shared::cluster address is cleared).
+template <int CG>
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
                                             int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
-               : "memory");
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -99,18 +136,36 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// arrive on `bar` once every MMA issued so far has retired; CG == 2: on the same barrier of both CTAs
+template <int CG>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3)
+        : "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (CG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t gets lane (base_lane + t), columns col..col+31
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
@@ -155,55 +210,76 @@ __device__ __forceinline__ constexpr uint32_t kslice_bytes() {
   return KMAJOR ? UK * 2 : UK * 128;
 }
 // instruction descriptor: c=F32 [4,6), a=b=BF16 [7,10),[10,13), a_major 15, b_major 16,
-// N>>3 [17,23), M>>4 [24,29)
-template <int BN, bool AK, bool BKM>
+// N>>3 [17,23), M>>4 [24,29).  M = 128 per CTA of the group (256 for cta_group::2).
+template <int BN, int CG, bool AK, bool BKM>
 __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((AK ? 0u : 1u) << 15) | ((BKM ? 0u : 1u) << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
 }
 
 struct TcShape {
   int M, N, K, batch;
-  int mt, nt, num_kb;
+  int mt, nt, num_kb;       // mt counts (128*CG)-row tiles
+  int gm;                   // rasterisation band height in m-tiles
   int zA1, zB1, zA2, zB2;   // 0: the operand is shared by every batch index z (stride 0), 1: batched
 };
 
-template <int MODE, int BN>
+// Tile rasterisation: bands of `gm` m-tiles, inside a band n-major.  The ~#SM/CG tiles in flight
+// then form a gm x (slots/gm) block of the tile grid, so their A rows and B rows are shared
+// through L2 (M-fastest order streamed the whole A operand from DRAM once per wave: 1.05 GB read
+// for a 192 MB problem, ncu r01b).
+__device__ __forceinline__ void decode_tile(const TcShape& sh, int tile, int& mi, int& ni) {
+  const int band_tiles = sh.gm * sh.nt;
+  const int band = tile / band_tiles;
+  const int r = tile - band * band_tiles;
+  const int rows = min(sh.gm, sh.mt - band * sh.gm);
+  ni = r / rows;
+  mi = band * sh.gm + (r - ni * rows);
+}
+
+// CG = CTAs per MMA (cta_group).  With CG == 2 a CTA pair owns a (256 x BN) tile: CTA r holds rows
+// [128r, 128r+128) of A and of the accumulator and rows [r*BN/2, (r+1)*BN/2) of B; the leader
+// (rank 0) issues tcgen05.mma.cta_group::2, which reads both CTAs' shared memory.
+template <int MODE, int BN, int CG>
 struct TcCfg {
   static constexpr bool DUAL = epi_is_dual(MODE);
   static constexpr int NACC = DUAL ? 2 : 1;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_ROWS = BN / CG;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = NACC * (A_BYTES + B_BYTES);
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
-  static constexpr int ACC_COLS = NACC * BN;        // TMEM columns per accumulator stage
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;    // double-buffered
+  static constexpr int ACC_COLS = NACC * BN;                        // TMEM columns per accumulator stage
+  static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;    // double-buffered when it fits
+  static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
+  static_assert(B_ROWS % 64 == 0, "B tile rows per CTA must be a multiple of 64");
 };
 
 // One operand tile: K-major -> one {64 x ROWS} box; MN-major -> ROWS/64 boxes of {64 x BK}.
-template <bool KMAJOR, int ROWS>
+template <int CG, bool KMAJOR, int ROWS>
 __device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, uint32_t bar,
                                              int mn0, int k0, int z) {
   if constexpr (KMAJOR) {
-    tma_load_3d(dst, tm, bar, k0, mn0, z);
+    tma_load_3d<CG>(dst, tm, bar, k0, mn0, z);
   } else {
 #pragma unroll
-    for (int c = 0; c < ROWS / 64; ++c) tma_load_3d(dst + c * (BK * 128), tm, bar, mn0 + c * 64, k0, z);
+    for (int c = 0; c < ROWS / 64; ++c) tma_load_3d<CG>(dst + c * (BK * 128), tm, bar, mn0 + c * 64, k0, z);
   }
 }
 
-template <int MODE, int BN, bool AK, bool BKM>
+template <int MODE, int BN, int CG, bool AK, bool BKM>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                TcShape sh, EpiParams p) {
-  using C = TcCfg<MODE, BN>;
+  using C = TcCfg<MODE, BN, CG>;
   constexpr bool DUAL = C::DUAL;
   constexpr bool ZACC = epi_z_accumulates(MODE);
+  constexpr int AS = C::ACC_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -216,44 +292,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;     // position inside the CTA pair
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1);
     tma_prefetch_desc(&tmB1);
     if (DUAL) { tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB2); }
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPIW); }
+    // the leader's MMA thread waits for the epilogue warps of every CTA of the group
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPIW * CG); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 1) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int tiles = sh.mt * sh.nt;
   const int num_work = ZACC ? tiles : tiles * sh.batch;
+  const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
 
   if (warp == 0) {
-    // ======================= TMA producer =======================
+    // ======================= TMA producer (one per CTA) =======================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = group; w < num_work; w += num_groups) {
         const int tile = ZACC ? w : w % tiles;
         const int zb = ZACC ? 0 : w / tiles, zn = ZACC ? sh.batch : 1;
-        const int m0 = (tile % sh.mt) * BM, n0 = (tile / sh.mt) * BN;
+        int mi, ni;
+        decode_tile(sh, tile, mi, ni);
+        const int m0 = mi * (BM * CG) + rank * BM;
+        const int n0 = ni * BN + rank * C::B_ROWS;
         for (int z = zb; z < zb + zn; ++z) {
           for (int kb = 0; kb < sh.num_kb; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1);
-            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            // the leader arms its barrier for the bytes of the whole group
+            if (leader) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES * CG);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
             const uint32_t sb = sa + C::NACC * C::A_BYTES;
-            load_operand<AK, BM>(&tmA1, sa, full_bar(stage), m0, kb * BK, z * sh.zA1);
-            load_operand<BKM, BN>(&tmB1, sb, full_bar(stage), n0, kb * BK, z * sh.zB1);
+            load_operand<CG, AK, BM>(&tmA1, sa, full_bar(stage), m0, kb * BK, z * sh.zA1);
+            load_operand<CG, BKM, C::B_ROWS>(&tmB1, sb, full_bar(stage), n0, kb * BK, z * sh.zB1);
             if (DUAL) {
-              load_operand<AK, BM>(&tmA2, sa + C::A_BYTES, full_bar(stage), m0, kb * BK, z * sh.zA2);
-              load_operand<BKM, BN>(&tmB2, sb + C::B_BYTES, full_bar(stage), n0, kb * BK, z * sh.zB2);
+              load_operand<CG, AK, BM>(&tmA2, sa + C::A_BYTES, full_bar(stage), m0, kb * BK, z * sh.zA2);
+              load_operand<CG, BKM, C::B_ROWS>(&tmB2, sb + C::B_BYTES, full_bar(stage), n0, kb * BK, z * sh.zB2);
             }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
@@ -261,12 +345,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer (one thread) =======================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN, AK, BKM>();
+    // ======================= MMA issuer (one thread of the leader CTA) =======================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc<BN, CG, AK, BKM>();
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = group; w < num_work; w += num_groups) {
         const int zn = ZACC ? sh.batch : 1;
         for (int zi = 0; zi < zn; ++zi) {
           mbar_wait(tempty_bar(as), aphase ^ 1);
@@ -280,29 +364,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {
               const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-              umma_bf16(d1, make_sdesc<AK>(sa + k * kslice_bytes<AK>()),
-                        make_sdesc<BKM>(sb + k * kslice_bytes<BKM>()), idesc, acc);
+              umma_bf16<CG>(d1, make_sdesc<AK>(sa + k * kslice_bytes<AK>()),
+                            make_sdesc<BKM>(sb + k * kslice_bytes<BKM>()), idesc, acc);
               if (DUAL)
-                umma_bf16(d1 + BN, make_sdesc<AK>(sa + C::A_BYTES + k * kslice_bytes<AK>()),
-                          make_sdesc<BKM>(sb + C::B_BYTES + k * kslice_bytes<BKM>()), idesc, acc);
+                umma_bf16<CG>(d1 + BN, make_sdesc<AK>(sa + C::A_BYTES + k * kslice_bytes<AK>()),
+                              make_sdesc<BKM>(sb + C::B_BYTES + k * kslice_bytes<BKM>()), idesc, acc);
             }
-            tc_commit(empty_bar(stage));     // smem slot free once these MMAs retire
+            tc_commit<CG>(empty_bar(stage));     // smem slot free (in every CTA) once these MMAs retire
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(tfull_bar(as));          // accumulator ready for the epilogue
-          if (++as == 2) { as = 0; aphase ^= 1; }
+          tc_commit<CG>(tfull_bar(as));          // accumulator ready for the epilogue warps
+          if (++as == AS) { as = 0; aphase ^= 1; }
         }
       }
     }
   } else {
-    // ======================= epilogue warps =======================
+    // ======================= epilogue warps (every CTA drains its own 128 TMEM lanes) ==========
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;        // two warps share a quarter, split the columns
+    const PhiloxStream ps = epi_stream(p);
     int as = 0; uint32_t aphase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    for (int w = group; w < num_work; w += num_groups) {
       const int tile = ZACC ? w : w % tiles;
       const int zb = ZACC ? 0 : w / tiles, zn = ZACC ? sh.batch : 1;
-      const int m0 = (tile % sh.mt) * BM, n0 = (tile / sh.mt) * BN;
+      int mi, ni;
+      decode_tile(sh, tile, mi, ni);
+      const int m0 = mi * (BM * CG) + rank * BM, n0 = ni * BN;
       const int row = m0 + q * 32 + lane;
       for (int z = zb; z < zb + zn; ++z) {
         mbar_wait(tfull_bar(as), aphase);
@@ -317,24 +404,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            epi_quad<MODE, bf16>(p, z, row, n0 + c * 32 + j * 4,
+            epi_quad<MODE, bf16>(p, ps, z, row, n0 + c * 32 + j * 4,
                                  *reinterpret_cast<const float(*)[4]>(&v1[j * 4]),
                                  *reinterpret_cast<const float(*)[4]>(&v2[DUAL ? j * 4 : 0]));
           }
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
-        if (++as == 2) { as = 0; aphase ^= 1; }
+        if (lane == 0) {
+          if constexpr (CG == 1) mbar_arrive(tempty_bar(as));
+          else mbar_arrive_remote(tempty_bar(as), 0);      // the leader's barrier
+        }
+        if (++as == AS) { as = 0; aphase ^= 1; }
       }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -388,25 +478,33 @@ int make_tmap(CUtensorMap* tm, const TcOperand& op, int rows_mn, int K, int batc
   return VBNN_OK;
 }
 
+struct TcChoice { int bn, cg; };
 int g_block_n_override = 0;
+int g_cg_override = 0;
 
-template <int MODE, int BN, bool AK, bool BKM>
+template <int MODE, int BN, int CG, bool AK, bool BKM>
 int launch_cfg(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
-  using C = TcCfg<MODE, BN>;
+  using C = TcCfg<MODE, BN, CG>;
   TcShape sh;
   sh.M = g.M; sh.N = g.N; sh.K = g.K; sh.batch = g.batch;
-  sh.mt = ceil_div(g.M, BM); sh.nt = ceil_div(g.N, BN); sh.num_kb = ceil_div(g.K, BK);
+  sh.mt = ceil_div(g.M, BM * CG); sh.nt = ceil_div(g.N, BN); sh.num_kb = ceil_div(g.K, BK);
   sh.zA1 = g.A1.zs != 0; sh.zB1 = g.B1.zs != 0; sh.zA2 = g.A2.zs != 0; sh.zB2 = g.B2.zs != 0;
+  {
+    static int gm_env = -1;
+    if (gm_env < 0) { const char* e = getenv("VBNN_TC_GM"); gm_env = e ? atoi(e) : 0; }
+    sh.gm = gm_env > 0 ? gm_env : 8;
+    if (sh.gm > sh.mt) sh.gm = sh.mt;
+  }
   CUtensorMap tA1, tB1, tA2, tB2;
   VB_TRY(make_tmap(&tA1, g.A1, g.M, g.K, g.batch, BM));
-  VB_TRY(make_tmap(&tB1, g.B1, g.N, g.K, g.batch, BN));
+  VB_TRY(make_tmap(&tB1, g.B1, g.N, g.K, g.batch, C::B_ROWS));
   if (C::DUAL) {
     VB_TRY(make_tmap(&tA2, g.A2, g.M, g.K, g.batch, BM));
-    VB_TRY(make_tmap(&tB2, g.B2, g.N, g.K, g.batch, BN));
+    VB_TRY(make_tmap(&tB2, g.B2, g.N, g.K, g.batch, C::B_ROWS));
   } else {
     tA2 = tA1; tB2 = tB1;
   }
-  auto kern = gemm_tc_kernel<MODE, BN, AK, BKM>;
+  auto kern = gemm_tc_kernel<MODE, BN, CG, AK, BKM>;
   static bool attr_set = false;
   if (!attr_set) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -414,37 +512,55 @@ int launch_cfg(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
   }
   const int tiles = sh.mt * sh.nt;
   const int num_work = epi_z_accumulates(MODE) ? tiles : tiles * g.batch;
-  int dev = 0, sms = kNumSMs;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = num_work < sms ? num_work : sms;
-  kern<<<grid, NTHREADS, C::SMEM_BYTES, st>>>(tA1, tB1, tA2, tB2, sh, p);
-  VB_CUDA(cudaGetLastError());
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = kNumSMs;
+  }
+  const int groups = num_work < sms / CG ? num_work : sms / CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups * CG);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VB_CUDA(cudaLaunchKernelEx(&cfg, kern, tA1, tB1, tA2, tB2, sh, p));
   return VBNN_OK;
 }
 
-// Pick BLOCK_N for the single-accumulator modes: the wider tile halves the per-flop smem/L2
-// traffic, the narrower one quantises better on small problems.
+// Tile choice.  A CTA pair (cta_group::2) on a 256 x 256 tile halves the operand traffic per MAC
+// (the 128 x 128 tile needs more L2->SM bandwidth than the chip has), so it wins whenever the
+// problem has enough 256 x 256 tiles to fill the 74 pairs; small problems quantise better on
+// 128 x 128 single-CTA tiles.  cost = waves x (tile MACs / relative per-MAC speed).
+template <int MODE>
+TcChoice choose_cfg(const TcGemmArgs& g) {
+  TcChoice c{g_block_n_override, g_cg_override};
+  if (!c.bn) { const char* e = getenv("VBNN_TC_BN"); if (e) c.bn = atoi(e); }      // debugging knobs
+  if (!c.cg) { const char* e = getenv("VBNN_TC_CG"); if (e) c.cg = atoi(e); }
+  if ((c.bn == 128 || c.bn == 256) && (c.cg == 1 || c.cg == 2) && !(c.bn == 128 && c.cg == 2)) return c;
+  const long long zmul = epi_z_accumulates(MODE) ? 1 : g.batch;
+  auto cost = [&](int bn, int cg, double speed) {
+    const long long work = (long long)ceil_div(g.M, BM * cg) * ceil_div(g.N, bn) * zmul;
+    const long long slots = kNumSMs / cg;
+    const long long waves = (work + slots - 1) / slots;
+    return (double)waves * (double)bn / speed;      // each CTA computes 128 x bn per tile
+  };
+  const double c1 = cost(128, 1, 1.0), c2 = cost(256, 2, 1.45);
+  return c2 <= c1 ? TcChoice{256, 2} : TcChoice{128, 1};
+}
+
 template <int MODE, bool AK, bool BKM>
-int launch_single(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
-  int bn = g_block_n_override;
-  if (bn == 0) {
-    const char* env = getenv("VBNN_TC_BN");      // debugging knob (tools/gemm_probe.py)
-    if (env) bn = atoi(env);
-  }
-  if (bn != 128 && bn != 256) bn = 0;
-  if (bn == 0) {
-    const int mt = ceil_div(g.M, BM);
-    const long long zmul = epi_z_accumulates(MODE) ? 1 : g.batch;
-    const long long w256 = (long long)mt * ceil_div(g.N, 256) * zmul;
-    const long long w128 = (long long)mt * ceil_div(g.N, 128) * zmul;
-    // waves * tile cost (256-wide tile costs 2 units)
-    const long long c256 = ((w256 + kNumSMs - 1) / kNumSMs) * 2;
-    const long long c128 = ((w128 + kNumSMs - 1) / kNumSMs) * 1;
-    bn = (g.N > 128 && c256 <= c128) ? 256 : 128;
-  }
-  if (bn == 256) return launch_cfg<MODE, 256, AK, BKM>(g, p, st);
-  return launch_cfg<MODE, 128, AK, BKM>(g, p, st);
+int launch_any(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
+  const TcChoice c = choose_cfg<MODE>(g);
+  if (c.cg == 2) return launch_cfg<MODE, 256, 2, AK, BKM>(g, p, st);
+  if (c.bn == 256 && !epi_is_dual(MODE)) return launch_cfg<MODE, epi_is_dual(MODE) ? 128 : 256, 1, AK, BKM>(g, p, st);
+  return launch_cfg<MODE, 128, 1, AK, BKM>(g, p, st);
 }
 
 }  // namespace
@@ -459,28 +575,28 @@ int gemm_tc_launch(int mode, const TcGemmArgs& g, const EpiParams& p, cudaStream
   const bool ak = g.A1.kmajor != 0, bk = g.B1.kmajor != 0;
   switch (mode) {
     case EPI_STORE:
-      if (ak && bk) return launch_single<EPI_STORE, true, true>(g, p, st);
-      if (ak && !bk) return launch_single<EPI_STORE, true, false>(g, p, st);
-      if (!ak && bk) return launch_single<EPI_STORE, false, true>(g, p, st);
-      return launch_single<EPI_STORE, false, false>(g, p, st);
+      if (ak && bk) return launch_any<EPI_STORE, true, true>(g, p, st);
+      if (ak && !bk) return launch_any<EPI_STORE, true, false>(g, p, st);
+      if (!ak && bk) return launch_any<EPI_STORE, false, true>(g, p, st);
+      return launch_any<EPI_STORE, false, false>(g, p, st);
     case EPI_FWD:
       VB_CHECK(ak && bk, VBNN_E_INVALID, "EPI_FWD expects K-major operands");
-      return launch_single<EPI_FWD, true, true>(g, p, st);
+      return launch_any<EPI_FWD, true, true>(g, p, st);
     case EPI_FWD_LRT:
       VB_CHECK(ak && bk, VBNN_E_INVALID, "EPI_FWD_LRT expects K-major operands");
-      return launch_cfg<EPI_FWD_LRT, 128, true, true>(g, p, st);
+      return launch_any<EPI_FWD_LRT, true, true>(g, p, st);
     case EPI_DX:
       VB_CHECK(ak && !bk, VBNN_E_INVALID, "EPI_DX expects K-major A, MN-major B");
-      return launch_single<EPI_DX, true, false>(g, p, st);
+      return launch_any<EPI_DX, true, false>(g, p, st);
     case EPI_DX_LRT:
       VB_CHECK(ak && !bk, VBNN_E_INVALID, "EPI_DX_LRT expects K-major A, MN-major B");
-      return launch_cfg<EPI_DX_LRT, 128, true, false>(g, p, st);
+      return launch_any<EPI_DX_LRT, true, false>(g, p, st);
     case EPI_DW:
       VB_CHECK(!ak && !bk, VBNN_E_INVALID, "EPI_DW expects MN-major operands");
-      return launch_single<EPI_DW, false, false>(g, p, st);
+      return launch_any<EPI_DW, false, false>(g, p, st);
     case EPI_DW_LRT:
       VB_CHECK(!ak && !bk, VBNN_E_INVALID, "EPI_DW_LRT expects MN-major operands");
-      return launch_cfg<EPI_DW_LRT, 128, false, false>(g, p, st);
+      return launch_any<EPI_DW_LRT, false, false>(g, p, st);
   }
   set_error("gemm_tc_launch: bad mode %d", mode);
   return VBNN_E_INVALID;

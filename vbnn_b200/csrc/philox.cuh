@@ -65,7 +65,8 @@ __device__ __forceinline__ void philox_normal4(const PhiloxStream& ps, uint32_t 
 #pragma unroll
   for (int a = 0; a < 4; a += 2) {
     float u0 = u32_to_unit(c[a]), u1 = u32_to_unit(c[a + 1]);
-    float r = sqrtf(-2.0f * __logf(u0));
+    float t = -2.0f * __logf(u0);          // >= 0; exactly 0 when u0 rounds to 1.0 (p ~ 2^-25)
+    float r = t * rsqrtf(fmaxf(t, 1e-30f)); // sqrt via MUFU.RSQ (no IEEE slow path), 0 -> 0
     float s, co;
     __sincosf(6.283185307179586f * u1, &s, &co);
     n[a] = r * co;
