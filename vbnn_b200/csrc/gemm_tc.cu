@@ -17,6 +17,7 @@
 // {64 x BK} boxes and handed to the MMA through an MN-major shared-memory descriptor, so the
 // batch-contracting dW GEMM (D = G^T X) and dX = G W need no transposed copies.
 #include "gemm.h"
+#include "epilogue_tc.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -31,7 +32,8 @@ constexpr int BK = 64;    // one 128-byte swizzle row of bf16
 constexpr int UK = 16;    // UMMA K for 16-bit inputs
 constexpr int EPIW = 8;   // epilogue warps
 constexpr int NTHREADS = (2 + EPIW) * 32;
-constexpr int SMEM_BUDGET = 227 * 1024 - 2048;   // minus barriers + alignment slack
+constexpr int EPI_STAGE_BYTES = EPIW * kStageBytes;            // per-warp epilogue staging tiles
+constexpr int SMEM_BUDGET = 227 * 1024 - 2048 - EPI_STAGE_BYTES;   // minus barriers + alignment slack + staging
 
 // ------------------------------------------------------------------ PTX wrappers ---------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -221,6 +223,7 @@ struct TcShape {
   int M, N, K, batch;
   int mt, nt, num_kb;       // mt counts (128*CG)-row tiles
   int gm;                   // rasterisation band height in m-tiles
+  int staged;               // every epilogue tensor is 16-byte aligned: coalesced staged I/O
   int zA1, zB1, zA2, zB2;   // 0: the operand is shared by every batch index z (stride 0), 1: batched
 };
 
@@ -253,7 +256,7 @@ struct TcCfg {
   static constexpr int ACC_COLS = NACC * BN;                        // TMEM columns per accumulator stage
   static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;    // double-buffered when it fits
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 2048;
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
   static_assert(B_ROWS % 64 == 0, "B tile rows per CTA must be a multiple of 64");
@@ -283,7 +286,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t epi_stage_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = epi_stage_base + EPI_STAGE_BYTES;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM address
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
@@ -383,6 +387,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;        // two warps share a quarter, split the columns
     const PhiloxStream ps = epi_stream(p);
+    const uint32_t my_stage = epi_stage_base + (uint32_t)(warp - 2) * kStageBytes;
     int as = 0; uint32_t aphase = 0;
     for (int w = group; w < num_work; w += num_groups) {
       const int tile = ZACC ? w : w % tiles;
@@ -402,11 +407,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           tmem_ld32(t0 + c * 32, v1);
           if (DUAL) tmem_ld32(t0 + BN + c * 32, v2);
           tmem_ld_wait();
+          if (sh.staged && n0 + c * 32 + 32 <= sh.N) {
+            epi_chunk_staged<MODE>(p, ps, z, m0 + q * 32, lane, n0 + c * 32, v1, v2, my_stage);
+          } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            epi_quad<MODE, bf16>(p, ps, z, row, n0 + c * 32 + j * 4,
-                                 *reinterpret_cast<const float(*)[4]>(&v1[j * 4]),
-                                 *reinterpret_cast<const float(*)[4]>(&v2[DUAL ? j * 4 : 0]));
+            for (int j = 0; j < 8; ++j) {
+              epi_quad<MODE, bf16>(p, ps, z, row, n0 + c * 32 + j * 4,
+                                   *reinterpret_cast<const float(*)[4]>(&v1[j * 4]),
+                                   *reinterpret_cast<const float(*)[4]>(&v2[DUAL ? j * 4 : 0]));
+            }
           }
         }
         tc_fence_before();
@@ -494,6 +503,9 @@ int launch_cfg(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
     if (gm_env < 0) { const char* e = getenv("VBNN_TC_GM"); gm_env = e ? atoi(e) : 0; }
     sh.gm = gm_env > 0 ? gm_env : 8;
     if (sh.gm > sh.mt) sh.gm = sh.mt;
+    static int st_env = -1;
+    if (st_env < 0) { const char* e = getenv("VBNN_TC_STAGED"); st_env = e ? atoi(e) : 1; }
+    sh.staged = st_env && epi_can_stage(MODE, p);
   }
   CUtensorMap tA1, tB1, tA2, tB2;
   VB_TRY(make_tmap(&tA1, g.A1, g.M, g.K, g.batch, BM));
