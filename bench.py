@@ -76,7 +76,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -93,7 +93,7 @@ class ClockSampler:
     def summary(self, t0, t1):
         if self.proc:
             self.proc.terminate()
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, reasons, pw = [], 0.0, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for t, line in self.rows:
             f = [x.strip() for x in line.split(",")]
@@ -106,12 +106,17 @@ class ClockSampler:
             mx = max(mx, m)
             if t0 - 0.05 <= t <= t1 + 0.05:
                 sm.append(c)
+                try:
+                    pw.append(float(f[2]))
+                except ValueError:
+                    pass
                 for n, v in zip(names, f[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
         if not sm:
             sm = [float(l.split(",")[0]) for _, l in self.rows[-3:] if l and l.split(",")[0].strip().replace(".", "").isdigit()] or [0.0]
-        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=statistics.median(sm), sm_min_mhz=min(sm), sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm), power_w_max=max(pw) if pw else None)
 
 
 def build_net(w, ctx, N):
@@ -193,9 +198,9 @@ def main():
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.steps is None:
-        args.steps = 3 if args.impl == "reference" else (30 if args.workload == "c3" else 200)
+        args.steps = 3 if args.impl == "reference" else (200 if args.workload == "c3" else 500)
     if args.warmup is None:
-        args.warmup = 1 if args.impl == "reference" else (5 if args.workload == "c3" else 20)
+        args.warmup = 1 if args.impl == "reference" else (10 if args.workload == "c3" else 20)
     if args.impl == "reference":
         return run_reference(args, w)
     args.warmup = max(args.warmup, 3)

@@ -275,3 +275,45 @@ def test_full_size_bf16_tensor_core_path(ctx, sizes, N, S, reparam):
         assert rel(a, b) < 0.15
     for a, b in zip(out["bf16"][3], out["fp32"][3]):
         assert rel(a, b) < 2e-2
+
+
+def test_checkpoint_resume_is_exact(ctx):
+    """export after 2 minibatches, load into a fresh net, continue -- identical to the
+    uninterrupted run (parameters, Adam state, step counters, quirk-Q1 sigma cache all restored)."""
+    rng = np.random.RandomState(12)
+    X = torch.from_numpy(rng.randn(32, 40)).float().cuda()
+    T = torch.from_numpy(rng.randint(1, 7, 32).astype(np.float32)).cuda()
+    ctx.set_step(0)
+    a, _, _, _ = build_pair(ctx, [40, 48, 36, 6], 32, 2, 30.0, "fp32", "weight", seed=2)
+    for _ in range(2):
+        a.train_step(X, T)
+    sd = a.state_dict()
+    ra = [a.train_step(X, T) for _ in range(3)]
+    ma = cpu(a.model[0].means).copy()
+    b, _, _, _ = build_pair(ctx, [40, 48, 36, 6], 32, 2, 30.0, "fp32", "weight", seed=99)
+    b.load_state_dict(sd)
+    rb = [b.train_step(X, T) for _ in range(3)]
+    assert np.allclose(np.array(ra), np.array(rb), rtol=1e-6, atol=1e-7)
+    assert rel(cpu(b.model[0].means), ma) < 1e-7
+    assert b.model[0].t == a.model[0].t == 5
+
+
+def test_epoch_loops_device_resident(ctx):
+    """main:train / main:test (main.lua:13-74) over a device-resident synthetic
+    MNIST-shaped dataset; the fused loop and the step-by-step reference-order loop agree."""
+    import vbnn_b200
+    from vbnn_b200 import train as tr
+    res = []
+    for fused in (True, False):
+        ctx.set_step(0)
+        opt = vbnn_b200.default_opt(hidden=[32], S=2, B=8.0, batchSize=50, testBatchSize=100, trainSize=400,
+                                    testSize=200, mu_init=1, msr_init=True, log=False, testSamples=3,
+                                    meanState=dict(learningRate=0.002))
+        net = vbnn_b200.MLP(opt, ctx, max_batch=100)
+        net.init_params(seed=4, he_means=True)
+        ds = tr.synthetic_dataset(400, 784, 10, seed=3, geometry=(28, 28))
+        acc, err = tr.train(net, ds, opt, fused=fused, shuffle_seed=1)
+        tacc, terr = tr.test(net, dict(inputs=ds["inputs"][:200], targets=ds["targets"][:200]), opt)
+        assert math.isfinite(err) and 0.0 <= acc <= 100.0 and math.isfinite(terr) and 0.0 <= tacc <= 100.0
+        res.append((acc, err, tacc, terr))
+    assert np.allclose(res[0], res[1], rtol=1e-4, atol=1e-4)

@@ -95,6 +95,7 @@ extern "C" int vbnn_comm_init(vbnn_ctx* ctx, const void* id128, int rank, int nr
   ctx->nccl_comm = comm;
   ctx->rank = rank;
   ctx->nranks = nranks;
+  if (!ctx->comm_stream) VB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   return VBNN_OK;
 }
 
@@ -105,6 +106,7 @@ extern "C" int vbnn_comm_destroy(vbnn_ctx* ctx) {
   ctx->nccl_comm = nullptr;
   ctx->rank = 0;
   ctx->nranks = 1;
+  if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); ctx->comm_stream = nullptr; }
   return VBNN_OK;
 }
 

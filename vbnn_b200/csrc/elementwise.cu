@@ -96,8 +96,10 @@ __global__ void __launch_bounds__(kThreads) k_sample_w(SampleParams p) {
 // VBLinear.lua:78-86: exp, sqrt, add, pow, add, sum + D2H sync  ->  one read pass, no sync.
 __global__ void __launch_bounds__(kThreads) k_prior_partials(const float* __restrict__ mu,
                                                              const float* __restrict__ lvar,
-                                                             long long n, double* partials) {
+                                                             long long n, double* partials,
+                                                             const int* t_dev) {
   __shared__ double sh[32];
+  if (t_dev) partials += (size_t)(*t_dev & 1) * kMaxPartials;
   float acc = 0.f;
   double dacc = 0.0;
   const long long n4 = n >> 2;
@@ -151,16 +153,18 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateParams p) {
   __shared__ double sh[32];
   __shared__ float s_var_hat;
   __shared__ AdamCoef s_coef;
+  const int t_now = *p.t_dev;
   {
+    const double* part = p.partials + (p.partials_pingpong ? (size_t)(t_now & 1) * kMaxPartials : 0);
     double a = 0.0;
-    for (int i = threadIdx.x; i < p.n_partials; i += blockDim.x) a += p.partials[i];
+    for (int i = threadIdx.x; i < p.n_partials; i += blockDim.x) a += part[i];
     double r = block_sum(a, sh);
     if (threadIdx.x == 0) {
       const long long W = (long long)p.O * p.I;
       float vh = (float)(r / (double)W);
       s_var_hat = vh;
       if (blockIdx.x == 0) *p.var_hat_dev = vh;
-      const int t = *p.t_dev + 1;                                       // state.t = state.t + 1
+      const int t = t_now + 1;                                          // state.t = state.t + 1
       double bc1 = 1.0 - pow((double)p.beta1, (double)t);
       double bc2 = 1.0 - pow((double)p.beta2, (double)t);
       s_coef.step_mu = (float)((double)p.lr_mu * sqrt(bc2) / bc1);
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateParams p) {
   const float inv_vh = 1.f / var_hat;
   const float b1 = p.beta1, b2 = p.beta2, omb1 = 1.f - p.beta1, omb2 = 1.f - p.beta2;
 
+  float nxt = 0.f;                       // sigma_hat^2 numerator of the next minibatch
   double st[kStatSlots];
   if (STATS) {
 #pragma unroll
@@ -227,6 +232,7 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateParams p) {
       mu[j] += dmu;
       lv[j] += dlv;
       s2_new[j] = __expf(lv[j]);
+      if (j < nv) nxt += s2_new[j] + mu[j] * mu[j];
       if (STATS && j < nv) {
         st[0] += (double)vlcg * vlcg; st[1] += (double)vleg * vleg;
         st[2] += (double)mlcg * mlcg; st[3] += (double)mleg * mleg;
@@ -252,6 +258,11 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateParams p) {
         for (int j = 0; j < nv; ++j) { d1[j] = __float2bfloat16_rn(mu[j]); d2[j] = __float2bfloat16_rn(s2_new[j]); }
       }
     }
+  }
+  if (p.next_partials) {
+    double r = block_sum((double)nxt, sh);
+    if (threadIdx.x == 0)
+      p.next_partials[(p.partials_pingpong ? (size_t)((t_now + 1) & 1) * kMaxPartials : 0) + blockIdx.x] = r;
   }
   if (STATS) {
     // sums in slots 0..9, min/max in 11..14
@@ -571,9 +582,22 @@ int launch_prior_partials(const float* mu, const float* lvar, long long n, doubl
                           int* n_partials_out, cudaStream_t st) {
   int grid = grid_for((n + 3) / 4, 4);
   if (grid > kMaxPartials) grid = kMaxPartials;
-  k_prior_partials<<<grid, kThreads, 0, st>>>(mu, lvar, n, partials);
+  k_prior_partials<<<grid, kThreads, 0, st>>>(mu, lvar, n, partials, nullptr);
   VB_CUDA(cudaGetLastError());
   *n_partials_out = grid;
+  return VBNN_OK;
+}
+
+int update_grid(int O, int I) {
+  const long long quads = (long long)O * ((I + 3) / 4);
+  int grid = grid_for(quads, 4);
+  return grid > kMaxPartials ? kMaxPartials : grid;
+}
+
+int launch_prior_partials_pp(const float* mu, const float* lvar, long long n, double* partials2,
+                             const int* t_dev, int grid, cudaStream_t st) {
+  k_prior_partials<<<grid, kThreads, 0, st>>>(mu, lvar, n, partials2, t_dev);
+  VB_CUDA(cudaGetLastError());
   return VBNN_OK;
 }
 
@@ -588,9 +612,7 @@ int launch_prior_finalize(const double* partials, int n_partials, long long W, f
 }
 
 int launch_update(const UpdateParams& p, int* grid_out, cudaStream_t st) {
-  const long long quads = (long long)p.O * ((p.I + 3) / 4);
-  int grid = grid_for(quads, 4);
-  if (grid > kMaxPartials) grid = kMaxPartials;
+  const int grid = update_grid(p.O, p.I);
   const bool vec = (p.I & 3) == 0;
   const bool stats = p.stat_partials != nullptr;
   if (vec && stats) k_update<true, true><<<grid, kThreads, 0, st>>>(p);

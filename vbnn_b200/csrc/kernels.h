@@ -26,6 +26,11 @@ int launch_sample_w(const SampleParams& p, cudaStream_t st);
 // VBLinear:compute_prior (VBLinear.lua:77-88): per-block partial sums of exp(lvar) + mu^2.
 int launch_prior_partials(const float* mu, const float* lvar, long long n, double* partials,
                           int* n_partials_out, cudaStream_t st);
+// same reduction with a fixed grid, written to the half of a 2 x kMaxPartials ping-pong buffer that
+// the next update of the layer will read: partials2 + (*t_dev & 1) * kMaxPartials
+int launch_prior_partials_pp(const float* mu, const float* lvar, long long n, double* partials2,
+                             const int* t_dev, int grid, cudaStream_t st);
+int update_grid(int O, int I);
 // finalise var_hat = sum / W into a device scalar (+ optional caches stdv, mu_sqe)
 int launch_prior_finalize(const double* partials, int n_partials, long long W, float* var_hat_dev,
                           const float* mu, const float* lvar, float* stdv, float* mu_sqe,
@@ -42,12 +47,15 @@ struct UpdateParams {
   float* s2_f32;                        // nullable: sigma^2 operand for the fp32 LRT path
   int O, I;
   const double* partials; int n_partials;
+  int partials_pingpong;                // partials / next_partials are 2 x kMaxPartials halves selected by (*t_dev & 1)
   float* var_hat_dev;                   // out: var_hat used by this update
   const int* t_dev;                     // Adam step counter (t BEFORE this update)
   float B, S;
   float lr_mu, lr_var, beta1, beta2, eps;
   int lrt;
   double* stat_partials;                // nullable [grid x kStatSlots]
+  double* next_partials;                // nullable [grid]: sum(exp(lvar_new) + mu_new^2) per block, i.e.
+                                        // the compute_prior partials of the NEXT update (saves a read pass)
 };
 int launch_update(const UpdateParams& p, int* grid_out, cudaStream_t st);
 

@@ -78,6 +78,16 @@ int layer_compute_prior_internal(vbnn_layer* L) {
   return VBNN_OK;
 }
 
+// (re)compute the ping-pong partial sums the next update will read; called whenever mu / lvar / t
+// change outside update() so that update() itself never needs a separate reduction pass
+int layer_refresh_prior_partials(vbnn_layer* L) {
+  if (L->kind != VBNN_KIND_VB) return VBNN_OK;
+  VB_TRY(launch_prior_partials_pp(L->means, L->lvars, (long long)L->O * L->I, L->prior_partials, L->t_dev,
+                                  update_grid(L->O, L->I), L->ctx->stream));
+  L->ctx->launches++;
+  return VBNN_OK;
+}
+
 int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts* opts, int S_alloc,
                           float* gW, float* gS, float* gb, int id, vbnn_layer** out) {
   VB_CHECK(ctx && out && opts, VBNN_E_INVALID, "layer_create: null argument");
@@ -108,6 +118,7 @@ int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts
     A_(dev_zalloc(&L->m_mu, W, st)); A_(dev_zalloc(&L->v_mu, W, st));
     A_(dev_zalloc(&L->m_var, W, st)); A_(dev_zalloc(&L->v_var, W, st));
     A_(dev_zalloc(&L->var_hat_dev, 1, st));
+    A_(dev_alloc(&L->prior_partials, (size_t)2 * kMaxPartials));
     if (opts->strict_reference) { A_(dev_alloc(&L->stdv, W)); A_(dev_alloc(&L->mu_sqe, W)); }
     if (!lrt && !b16) A_(dev_zalloc(&L->weight, W * L->S_alloc, st));
     if (!lrt && b16) A_(dev_zalloc(&L->w_bf16, (size_t)O * L->ldI * L->S_alloc, st));
@@ -127,6 +138,7 @@ int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts
     if (opts->mu_init == 0.f) VB_CUDA(cudaMemsetAsync(L->means, 0, W * 4, st));         // :23
     else VB_TRY(launch_init_normal(L->means, W, 0.f, sqrtf(var_init), layer_stream(L, kStreamInit, 0), st));  // :25-28
     VB_TRY(layer_compute_prior_internal(L));                                            // :46
+    VB_TRY(layer_refresh_prior_partials(L));
   } else {
     // nn.Linear weights as re-initialised by mlp.lua:47-55: N(0, sqrt(2/fan_in)), bias 0
     VB_TRY(launch_init_normal(L->weight, W, 0.f, sqrtf(2.0f / (float)I), layer_stream(L, kStreamInit, 0), st));
@@ -187,8 +199,8 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
     return VBNN_OK;
   }
   VB_TRY(launch_sgd(L->bias, L->gb, L->O, L->opts.lr_bias, nullptr, 1, 1, st));          // VBLinear.lua:125-128
-  int np = 0;
-  VB_TRY(launch_prior_partials(L->means, L->lvars, W, c->d_partials, &np, st));         // :130
+  // compute_prior (:130): the per-block sums of exp(lvar)+mu^2 were left behind by the previous
+  // update of this layer (or by layer_refresh_prior_partials after set / init)
   UpdateParams u;
   memset(&u, 0, sizeof(u));
   u.mu = L->means; u.lvar = L->lvars; u.gW = L->gW; u.gS = L->gS;
@@ -196,7 +208,8 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
   u.stdv = L->stdv; u.mu_sqe = L->mu_sqe;
   u.mu_bf16 = L->mu_bf16; u.s2_bf16 = L->s2_bf16; u.ld_bf16 = L->ldI; u.s2_f32 = L->s2_f32;
   u.O = L->O; u.I = L->I;
-  u.partials = c->d_partials; u.n_partials = np;
+  u.partials = L->prior_partials; u.n_partials = update_grid(L->O, L->I);
+  u.next_partials = L->prior_partials; u.partials_pingpong = 1;
   u.var_hat_dev = L->var_hat_dev; u.t_dev = L->t_dev;
   u.B = L->opts.B; u.S = (float)L->opts.S;
   u.lr_mu = L->opts.lr_mu; u.lr_var = L->opts.lr_var;
@@ -206,7 +219,7 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
   u.stat_partials = stat_dev;
   int grid = 0;
   VB_TRY(launch_update(u, &grid, st));                                                   // :131-143
-  c->launches += 3;
+  c->launches += 2;
   L->prior_valid = true;
   if (bump_t) {
     // single counter bump: the layer owns t_dev
@@ -215,6 +228,7 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
     int t = *reinterpret_cast<int*>(c->h_scalars) + 1;
     VB_CUDA(cudaMemcpyAsync(L->t_dev, &t, sizeof(int), cudaMemcpyHostToDevice, st));
     VB_CUDA(cudaStreamSynchronize(st));
+    // the kernel left the new sums in half ((t_old + 1) & 1) == (t & 1): consistent with the bump
   }
   if (stats) {
     VB_CUDA(cudaMemcpyAsync(c->h_partials, stat_dev, (size_t)grid * kStatSlots * sizeof(double),
@@ -399,7 +413,7 @@ extern "C" int vbnn_layer_destroy(vbnn_layer* L) {
   if (!L->grads_external) { DEV_FREE(L->gW); DEV_FREE(L->gS); DEV_FREE(L->gb); }
   DEV_FREE(L->m_mu); DEV_FREE(L->v_mu); DEV_FREE(L->m_var); DEV_FREE(L->v_var);
   DEV_FREE(L->eps); DEV_FREE(L->stdv); DEV_FREE(L->mu_sqe); DEV_FREE(L->s2_f32);
-  DEV_FREE(L->var_hat_dev); DEV_FREE(L->t_dev);
+  DEV_FREE(L->var_hat_dev); DEV_FREE(L->t_dev); DEV_FREE(L->prior_partials);
   DEV_FREE(L->w_bf16); DEV_FREE(L->mu_bf16); DEV_FREE(L->s2_bf16);
   DEV_FREE(L->xs); DEV_FREE(L->xs2); DEV_FREE(L->gs_); DEV_FREE(L->hs); DEV_FREE(L->R);
   DEV_FREE(L->zeta_keep);
@@ -715,6 +729,7 @@ extern "C" int vbnn_layer_set(vbnn_layer* L, int which, const float* src) {
   if (which == VBNN_BUF_MEANS || which == VBNN_BUF_LVARS || (which == VBNN_BUF_WEIGHT && L->kind == VBNN_KIND_LINEAR)) {
     VB_TRY(layer_refresh_copies(L));
     L->prior_valid = false;
+    VB_TRY(layer_refresh_prior_partials(L));
   }
   if (which == VBNN_BUF_WEIGHT && L->kind == VBNN_KIND_VB && L->w_bf16)
     VB_TRY(launch_cast(L->weight, L->I, L->O, L->I, L->w_bf16, nullptr, L->ldI, st));
@@ -731,7 +746,7 @@ extern "C" int vbnn_layer_set_t(vbnn_layer* L, int t) {
   VB_CHECK(L, VBNN_E_INVALID, "null argument");
   VB_CUDA(cudaMemcpyAsync(L->t_dev, &t, sizeof(int), cudaMemcpyHostToDevice, L->ctx->stream));
   VB_CUDA(cudaStreamSynchronize(L->ctx->stream));
-  return VBNN_OK;
+  return layer_refresh_prior_partials(L);
 }
 
 extern "C" int vbnn_layer_snr_count(vbnn_layer* L, float thresh, uint8_t* mask_dev, long long* count) {

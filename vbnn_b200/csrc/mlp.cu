@@ -241,21 +241,45 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
   return VBNN_OK;
 }
 
-int run_samples(vbnn_mlp* m, int N, int Zrun, int sample0, int accumulate, bool backward) {
+// reduce_overlap: data-parallel step -- the allreduce of layer j's {gW, gS, gb} slice starts on the
+// communication stream as soon as its dW is done and overlaps the backward of the layers below.
+int run_samples(vbnn_mlp* m, int N, int Zrun, int sample0, int accumulate, bool backward, bool reduce_overlap = false) {
   const int Lc = nlayers(m);
+  vbnn_ctx* c = m->ctx;
   for (int j = 0; j < Lc; ++j) VB_TRY(forward_layer(m, j, N, Zrun, sample0, false));
   VB_TRY(loss_all(m, N, Zrun, backward, nullptr, m->result_acc));
   if (backward)
-    for (int j = Lc - 1; j >= 0; --j) VB_TRY(backward_layer(m, j, N, Zrun, sample0, accumulate));
+    for (int j = Lc - 1; j >= 0; --j) {
+      VB_TRY(backward_layer(m, j, N, Zrun, sample0, accumulate));
+      if (reduce_overlap) {
+        VB_CUDA(cudaEventRecord(m->ev_bwd[j], c->stream));
+        VB_CUDA(cudaStreamWaitEvent(c->comm_stream, m->ev_bwd[j], 0));
+        VB_TRY(comm_allreduce_internal(c, m->grad_arena + m->grad_off[j], m->grad_len[j], c->comm_stream));
+        VB_CUDA(cudaEventRecord(m->ev_red[j], c->comm_stream));
+      }
+    }
   return VBNN_OK;
 }
 
-int update_all(vbnn_mlp* m) {
+int update_all(vbnn_mlp* m, bool wait_reduce = false) {
   const int Lc = nlayers(m);
-  // mlp.lua:117-142: SGD on the output layer first, then every VB layer in index order
-  if (m->layers[Lc - 1]->kind == VBNN_KIND_LINEAR) VB_TRY(layer_update_internal(m->layers[Lc - 1], nullptr, false));
-  for (vbnn_layer* L : m->layers)
-    if (L->kind == VBNN_KIND_VB) VB_TRY(layer_update_internal(L, nullptr, false));
+  cudaStream_t st = m->ctx->stream;
+  // mlp.lua:117-142: SGD on the output layer first, then the VB layers.  The layers are independent,
+  // so with the overlapped allreduce they are updated top-down, each as soon as its reduction lands.
+  if (m->layers[Lc - 1]->kind == VBNN_KIND_LINEAR) {
+    if (wait_reduce) VB_CUDA(cudaStreamWaitEvent(st, m->ev_red[Lc - 1], 0));
+    VB_TRY(layer_update_internal(m->layers[Lc - 1], nullptr, false));
+  }
+  if (wait_reduce) {
+    for (int j = Lc - 1; j >= 0; --j) {
+      if (m->layers[j]->kind != VBNN_KIND_VB) continue;
+      VB_CUDA(cudaStreamWaitEvent(st, m->ev_red[j], 0));
+      VB_TRY(layer_update_internal(m->layers[j], nullptr, false));
+    }
+  } else {
+    for (vbnn_layer* L : m->layers)
+      if (L->kind == VBNN_KIND_VB) VB_TRY(layer_update_internal(L, nullptr, false));
+  }
   return VBNN_OK;
 }
 
@@ -265,9 +289,13 @@ int step_body(vbnn_mlp* m, int N) {
   VB_CUDA(cudaMemsetAsync(m->result_acc, 0, (size_t)2 * m->Z * 4, st));
   for (vbnn_layer* L : m->layers) VB_CUDA(cudaMemsetAsync(L->gb, 0, (size_t)L->O * 4, st));   // main.lua:28
   VB_TRY(sample_all(m, 0, m->Z));                                                              // :33
-  VB_TRY(run_samples(m, N, m->Z, 0, /*accumulate=*/0, true));                                  // :34
-  if (m->ctx->nranks > 1) VB_TRY(comm_allreduce_internal(m->ctx, m->grad_arena, m->grad_count, st));
-  VB_TRY(update_all(m));                                                                       // :40
+  const bool dp = m->ctx->nranks > 1;
+  static int ov_env = -1;
+  if (ov_env < 0) { const char* e = getenv("VBNN_DP_OVERLAP"); ov_env = e ? atoi(e) : 1; }
+  const bool overlap = dp && ov_env && m->ctx->comm_stream != nullptr;
+  VB_TRY(run_samples(m, N, m->Z, 0, /*accumulate=*/0, true, overlap));                         // :34
+  if (dp && !overlap) VB_TRY(comm_allreduce_internal(m->ctx, m->grad_arena, m->grad_count, st));
+  VB_TRY(update_all(m, overlap));                                                              // :40
   VB_TRY(launch_finalize_result(m->result_acc, m->Z, N, m->result, st));                       // :38-39
   VB_TRY(launch_bump(m->ctx->d_step, m->t_list_dev, m->n_t, st));
   m->ctx->launches += 2;
@@ -338,6 +366,8 @@ extern "C" int vbnn_mlp_create(vbnn_ctx* ctx, const int* sizes, int n_sizes, int
     off_gW[j] = take(W);
     off_gS[j] = vb ? take(W) : 0;
     off_gb[j] = take(sizes[j + 1]);
+    m->grad_off.push_back(off_gW[j]);
+    m->grad_len.push_back(off - off_gW[j]);
   }
   m->grad_count = off;
   r = dalloc(&m->grad_arena, off * 4);
@@ -385,6 +415,12 @@ extern "C" int vbnn_mlp_create(vbnn_ctx* ctx, const int* sizes, int n_sizes, int
     if (r == VBNN_OK) cudaStreamSynchronize(st);
   }
   for (int s = 0; s < 2; ++s) { m->slots[s].busy = false; m->slots[s].h_result = nullptr; m->slots[s].copied = nullptr; }
+  for (int j = 0; j < Lc && r == VBNN_OK; ++j) {
+    cudaEvent_t a, b;
+    if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) { r = VBNN_E_CUDA; break; }
+    m->ev_bwd.push_back(a); m->ev_red.push_back(b);
+  }
   const char* env = getenv("VBNN_NO_GRAPH");
   if (env && env[0] == '1') m->use_graph = false;
   if (r != VBNN_OK) { vbnn_mlp_destroy(m); return r; }
@@ -398,6 +434,8 @@ extern "C" int vbnn_mlp_destroy(vbnn_mlp* m) {
   cudaStreamSynchronize(m->ctx->stream);
   cudaStreamSynchronize(m->ctx->copy_stream);
   if (m->graph) cudaGraphExecDestroy(m->graph);
+  for (cudaEvent_t e : m->ev_bwd) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_red) cudaEventDestroy(e);
   for (vbnn_layer* L : m->layers) vbnn_layer_destroy(L);
   for (void* p : m->act) if (p) cudaFree(p);
   for (void* p : m->act2) if (p) cudaFree(p);
@@ -448,6 +486,7 @@ extern "C" int vbnn_mlp_init_params(vbnn_mlp* m, uint64_t seed, int he_means) {
       else
         VB_CUDA(cudaMemsetAsync(L->means, 0, (size_t)W * 4, st));                  // VBLinear.lua:23
       VB_TRY(layer_compute_prior_internal(L));
+      VB_TRY(layer_refresh_prior_partials(L));
     }
     VB_TRY(layer_refresh_copies(L));
     m->ctx->launches += 2;

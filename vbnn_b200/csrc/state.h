@@ -27,6 +27,7 @@ struct vbnn_ctx {
   // data parallel
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
+  cudaStream_t comm_stream = nullptr;   // per-layer gradient allreduce overlaps the rest of backward
 };
 
 struct vbnn_layer {
@@ -43,6 +44,9 @@ struct vbnn_layer {
   float *m_mu = nullptr, *v_mu = nullptr, *m_var = nullptr, *v_var = nullptr;
   float *eps = nullptr, *stdv = nullptr, *mu_sqe = nullptr, *s2_f32 = nullptr;
   float* var_hat_dev = nullptr;
+  double* prior_partials = nullptr;  // 2 x kMaxPartials: per-block sums written by the last update (ping-pong:
+                                     // an update reads one half while its blocks write the other)
+  // half (t & 1) holds the sums of the CURRENT parameters, t = the layer's device step counter
   int* t_dev = nullptr;              // meanState.t == varState.t == biasState.evalCounter
   // bf16 tensor-core operand copies [.. x ldI]
   bf16 *w_bf16 = nullptr, *mu_bf16 = nullptr, *s2_bf16 = nullptr;
@@ -75,6 +79,8 @@ struct vbnn_mlp {
   float* result_acc = nullptr;       // [2*Z] loss sums / correct counts
   float* result = nullptr;           // [2] {error, accuracy}
   float* grad_arena = nullptr; size_t grad_count = 0;
+  std::vector<size_t> grad_off, grad_len;       // per-layer slice {gW, gS, gb} of the arena
+  std::vector<cudaEvent_t> ev_bwd, ev_red;      // dW of layer j done / its allreduce done
   int** t_list_dev = nullptr; int n_t = 0;
   // CUDA graph of one step, keyed by N
   cudaGraphExec_t graph = nullptr; int graph_N = -1; int eager_steps = 0; bool use_graph = true;
@@ -93,6 +99,7 @@ int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts
 int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t);
 int layer_refresh_copies(vbnn_layer* L);
 int layer_compute_prior_internal(vbnn_layer* L);
+int layer_refresh_prior_partials(vbnn_layer* L);
 PhiloxStream layer_stream(const vbnn_layer* L, uint32_t kind, int sample);
 int comm_allreduce_internal(vbnn_ctx* ctx, float* buf, size_t count, cudaStream_t st);
 // tensor-core GEMM launch with optional event bracketing (ctx->profiling)

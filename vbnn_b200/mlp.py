@@ -163,6 +163,42 @@ class MLP:
     def _last_n(self):
         return self.max_batch
 
+    # ---- checkpoint / resume (reference: u.safe_save(net) main.lua:181, utils.lua:73-80; resume
+    # main.lua:146-148).  The reference torch.save()s the whole object graph; here the device state
+    # is exported as a flat dict of CPU tensors (means, lvars, bias, Adam m/v/t per layer, the output
+    # layer, the Philox step counter) that torch.save / numpy can persist.
+    def state_dict(self):
+        sd = {"sizes": list(self.sizes), "step": self.ctx.get_step()}
+        names = [("means", L.BUF_MEANS), ("lvars", L.BUF_LVARS), ("bias", L.BUF_BIAS), ("m_mu", L.BUF_ADAM_M_MU),
+                 ("v_mu", L.BUF_ADAM_V_MU), ("m_var", L.BUF_ADAM_M_VAR), ("v_var", L.BUF_ADAM_V_VAR)]
+        for k, m in enumerate(self.model):
+            if m.kind == L.KIND_VB:
+                for n, b in names:
+                    sd[f"{k}.{n}"] = m.get(b)
+                if self.opt.get("strict_reference", True):
+                    sd[f"{k}.stdv"] = m.get(L.BUF_STDV)
+                    sd[f"{k}.mu_sqe"] = m.get(L.BUF_MU_SQE)
+            else:
+                sd[f"{k}.weight"] = m.get(L.BUF_WEIGHT)
+                sd[f"{k}.bias"] = m.get(L.BUF_BIAS)
+            sd[f"{k}.t"] = m.t
+        return sd
+
+    def load_state_dict(self, sd):
+        if list(sd["sizes"]) != list(self.sizes):
+            raise L.VbnnError(L.E_INVALID, f"checkpoint is for sizes {sd['sizes']}, net has {self.sizes}")
+        codes = dict(means=L.BUF_MEANS, lvars=L.BUF_LVARS, bias=L.BUF_BIAS, m_mu=L.BUF_ADAM_M_MU, v_mu=L.BUF_ADAM_V_MU,
+                     m_var=L.BUF_ADAM_M_VAR, v_var=L.BUF_ADAM_V_VAR, weight=L.BUF_WEIGHT, stdv=L.BUF_STDV,
+                     mu_sqe=L.BUF_MU_SQE)
+        for k, m in enumerate(self.model):
+            L.check(L.lib().vbnn_layer_set_t(m.handle, int(sd[f"{k}.t"])))
+            for n, b in codes.items():
+                if f"{k}.{n}" in sd:
+                    m.set(b, sd[f"{k}.{n}"])
+            if m.kind == L.KIND_VB and f"{k}.stdv" not in sd:
+                m.compute_prior()
+        self.ctx.set_step(int(sd["step"]))
+
     def launch_count(self):
         v = C.c_longlong()
         L.check(L.lib().vbnn_mlp_launch_count(self.handle, C.byref(v)))
