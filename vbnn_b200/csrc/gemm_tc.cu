@@ -67,6 +67,39 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
       ::"r"(bar), "r"(cta)
       : "memory");
 }
+// arm the barrier at the same offset in CTA `cta` of the cluster for `bytes` of async transactions
+__device__ __forceinline__ void mbar_expect_tx_remote(uint32_t bar, uint32_t cta, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}"
+      ::"r"(bar), "r"(cta), "r"(bytes)
+      : "memory");
+}
+// Cluster launch control (Blackwell): ask the hardware to cancel one not-yet-launched cluster of
+// this grid and hand its block index to us; the 16-byte response lands in every CTA of the cluster.
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp, uint32_t bar) {
+  asm volatile(
+      "clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+      ::"r"(resp), "r"(bar)
+      : "memory");
+}
+// returns the first blockIdx.x of the cancelled cluster, or -1 when nothing was left to cancel
+__device__ __forceinline__ int clc_read(uint32_t resp) {
+  uint32_t x, y, z, valid;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%4];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %3, 1, 0, p1;\n\t"
+      "mov.u32 %0, 0; mov.u32 %1, 0; mov.u32 %2, 0;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, r;\n\t}"
+      : "=r"(x), "=r"(y), "=r"(z), "=r"(valid)
+      : "r"(resp)
+      : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  return valid ? (int)x : -1;
+}
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -224,6 +257,7 @@ struct TcShape {
   int mt, nt, num_kb;       // mt counts (128*CG)-row tiles
   int gm;                   // rasterisation band height in m-tiles
   int staged;               // every epilogue tensor is 16-byte aligned: coalesced staged I/O
+  int clc;                  // dynamic scheduling: one cluster per work unit, resident clusters steal pending ones
   int zA1, zB1, zA2, zB2;   // 0: the operand is shared by every batch index z (stride 0), 1: batched
 };
 
@@ -294,6 +328,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  // cluster-launch-control ring (2 slots): 16-byte responses, full barriers (one per CTA), empty
+  // barriers (the leader's collect every consumer of the cluster)
+  auto clc_resp = [&](int s) { return bar_base + 256u + 16u * s; };
+  auto clc_full = [&](int s) { return bar_base + 320u + 8u * s; };
+  auto clc_empty = [&](int s) { return bar_base + 336u + 8u * s; };
+  constexpr uint32_t kClcConsumers = CG * (1 + EPIW) + 1;   // producers + epilogue warps of every CTA + the MMA thread
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CG == 2 ? (int)cluster_ctarank() : 0;     // position inside the CTA pair
@@ -306,6 +346,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     // the leader's MMA thread waits for the epilogue warps of every CTA of the group
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), EPIW * CG); }
+    for (int s = 0; s < 2; ++s) { mbar_init(clc_full(s), 1); mbar_init(clc_empty(s), kClcConsumers); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<CG>(tmem_slot, C::TMEM_COLS);
@@ -318,12 +359,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   const int tiles = sh.mt * sh.nt;
   const int num_work = ZACC ? tiles : tiles * sh.batch;
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
+  const bool dyn = sh.clc != 0;
+  // next work unit of a role: static round-robin, or the response of the CLC query issued by the
+  // leader's producer thread (every role consumes every response, including the final "nothing left")
+  auto next_work = [&](int w, int& cs, uint32_t& cp, bool whole_warp) -> int {
+    if (!dyn) { w += num_groups; return w < num_work ? w : -1; }
+    mbar_wait(clc_full(cs), cp);
+    const int first = clc_read(clc_resp(cs));
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || lane == 0) {
+      if (CG == 1 || leader) mbar_arrive(clc_empty(cs)); else mbar_arrive_remote(clc_empty(cs), 0);
+    }
+    if (++cs == 2) { cs = 0; cp ^= 1; }
+    return first >= 0 ? first / CG : -1;
+  };
 
   if (warp == 0) {
     // ======================= TMA producer (one per CTA) =======================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int w = group; w < num_work; w += num_groups) {
+      int cs = 0; uint32_t cp = 0;          // CLC ring position as consumer
+      int is = 0; uint32_t ip = 0;          // ... and as issuer (leader only)
+      for (int w = group; w >= 0 && w < num_work; w = next_work(w, cs, cp, false)) {
+        if (dyn && leader) {
+          // ask for the unit after this one now, so the answer is there when the loads are out
+          mbar_wait(clc_empty(is), ip ^ 1);
+          mbar_expect_tx(clc_full(is), 16);
+          if (CG == 2) mbar_expect_tx_remote(clc_full(is), 1, 16);
+          clc_try_cancel(clc_resp(is), clc_full(is));
+          if (++is == 2) { is = 0; ip ^= 1; }
+        }
         const int tile = ZACC ? w : w % tiles;
         const int zb = ZACC ? 0 : w / tiles, zn = ZACC ? sh.batch : 1;
         int mi, ni;
@@ -354,7 +419,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       constexpr uint32_t idesc = make_idesc<BN, CG, AK, BKM>();
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (int w = group; w < num_work; w += num_groups) {
+      int cs = 0; uint32_t cp = 0;
+      for (int w = group; w >= 0 && w < num_work; w = next_work(w, cs, cp, false)) {
         const int zn = ZACC ? sh.batch : 1;
         for (int zi = 0; zi < zn; ++zi) {
           mbar_wait(tempty_bar(as), aphase ^ 1);
@@ -389,7 +455,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     const PhiloxStream ps = epi_stream(p);
     const uint32_t my_stage = epi_stage_base + (uint32_t)(warp - 2) * kStageBytes;
     int as = 0; uint32_t aphase = 0;
-    for (int w = group; w < num_work; w += num_groups) {
+    int cs = 0; uint32_t cp = 0;
+    for (int w = group; w >= 0 && w < num_work; w = next_work(w, cs, cp, true)) {
       const int tile = ZACC ? w : w % tiles;
       const int zb = ZACC ? 0 : w / tiles, zn = ZACC ? sh.batch : 1;
       int mi, ni;
@@ -506,6 +573,9 @@ int launch_cfg(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
     static int st_env = -1;
     if (st_env < 0) { const char* e = getenv("VBNN_TC_STAGED"); st_env = e ? atoi(e) : 1; }
     sh.staged = st_env && epi_can_stage(MODE, p);
+    static int clc_env = -1;
+    if (clc_env < 0) { const char* e = getenv("VBNN_TC_CLC"); clc_env = e ? atoi(e) : 1; }
+    sh.clc = clc_env;
   }
   CUtensorMap tA1, tB1, tA2, tB2;
   VB_TRY(make_tmap(&tA1, g.A1, g.M, g.K, g.batch, BM));
@@ -531,7 +601,9 @@ int launch_cfg(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = kNumSMs;
   }
-  const int groups = num_work < sms / CG ? num_work : sms / CG;
+  // static: one persistent cluster per SM group; CLC: one cluster per work unit (the hardware keeps
+  // #SM/CG resident, the rest are cancelled and absorbed by the resident ones)
+  const int groups = sh.clc ? num_work : (num_work < sms / CG ? num_work : sms / CG);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(groups * CG);
   cfg.blockDim = dim3(NTHREADS);
