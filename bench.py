@@ -123,7 +123,8 @@ def build_net(w, ctx, N):
     import vbnn_b200
     s = w["sizes"]
     opt = vbnn_b200.default_opt(input_size=s[0], hidden=s[1:-1], classes=[str(i) for i in range(s[-1])],
-                                S=w["S"], B=w["B"], batchSize=N, testBatchSize=N, mu_init=1, msr_init=True,
+                                S=w["S"], B=w["B"], batchSize=N, testBatchSize=N, mu_init=1, msr_init=False,
+                                var_init=0.001,
                                 reparam=w["reparam"], precision=w["precision"], strict_reference=False, log=False,
                                 seed=5)
     net = vbnn_b200.MLP(opt, ctx, max_batch=N)
@@ -141,7 +142,7 @@ def cpu_baseline(w, threads, budget_rows=None):
     torch.set_num_threads(threads)
     s = w["sizes"]
     opt = O.default_opt(input_size=s[0], hidden=s[1:-1], classes=[str(i) for i in range(s[-1])], S=w["S"],
-                        B=w["B"], batchSize=w["N"], mu_init=1, msr_init=True, reparam=w["reparam"],
+                        B=w["B"], batchSize=w["N"], mu_init=1, msr_init=False, var_init=0.001, reparam=w["reparam"],
                         strict_reference=False)
     net = O.MLPOracle(opt, torch.float32, seed=3)
     rows = budget_rows or max(16, min(w["N"], int(2.0e11 / max(flops_per_sample(w), 1))))

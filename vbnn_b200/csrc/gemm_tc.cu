@@ -291,7 +291,7 @@ struct TcCfg {
   static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;    // double-buffered when it fits
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 2048;
-  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
   static_assert(B_ROWS % 64 == 0, "B tile rows per CTA must be a multiple of 64");
 };
@@ -463,6 +463,98 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       decode_tile(sh, tile, mi, ni);
       const int m0 = mi * (BM * CG) + rank * BM, n0 = ni * BN;
       const int row = m0 + q * 32 + lane;
+      if constexpr (ZACC && BN == 64) {
+        // Multi-sample dW (weight-space sampling, S > 1): this warp owns ONE 32 x 32 chunk of the
+        // tile and keeps its gradWeight / gradSum values in registers across all samples, so the
+        // per-sample work is TMEM load + Philox + FMA; global memory is touched once per tile
+        // (the per-sample read-modify-write was a ~1 us dependent chain per sample).
+        const int col0 = n0 + half * 32;
+        float accW[32], accS[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { accW[j] = 0.f; accS[j] = 0.f; }
+        const uint32_t qn = (uint32_t)((p.N + 3) >> 2);
+        for (int z = zb; z < zb + zn; ++z) {
+          mbar_wait(tfull_bar(as), aphase);
+          tc_fence_after();
+          const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS;
+          if (col0 < sh.N) {
+            float v1[32], v2[32];
+            tmem_ld32(t0 + half * 32, v1);
+            if (DUAL) tmem_ld32(t0 + BN + half * 32, v2);
+            tmem_ld_wait();
+            PhiloxStream psz = ps;
+            psz.sample += (uint32_t)z;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if constexpr (MODE == EPI_DW) {
+                float e[4];
+                if (p.noise) {
+                  const int cq = col0 + 4 * j;
+                  if (row < p.M && cq < p.N)
+                    load4<float>(p.noise + z * p.zs_noise + (long long)row * p.N + cq, e, min(4, p.N - cq), (p.N & 3) == 0);
+                  else e[0] = e[1] = e[2] = e[3] = 0.f;
+                } else {
+                  philox_normal4(psz, (uint32_t)row * qn + (uint32_t)((col0 >> 2) + j), e);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) accS[4 * j + k] += v1[4 * j + k] * e[k];     // VBLinear.lua:115
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) accS[4 * j + k] += v2[DUAL ? 4 * j + k : 0];
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) accW[4 * j + k] += p.scale * v1[4 * j + k];   // VBLinear.lua:113
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive(tempty_bar(as));
+            else mbar_arrive_remote(tempty_bar(as), 0);
+          }
+          if (++as == AS) { as = 0; aphase ^= 1; }
+        }
+        if (col0 < sh.N) {
+          const int row0 = m0 + q * 32;
+          const long long goff = (long long)row0 * p.ld_g + col0;
+          if (sh.staged && col0 + 32 <= sh.N) {
+            const int rows_valid = min(32, p.M - row0);
+            float t[32];
+            if (p.accumulate) {
+              get_tile_f32(my_stage, lane, p.gW + goff, p.ld_g, rows_valid, t);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) accW[j] += t[j];
+            }
+            put_tile_f32(my_stage, lane, p.gW + goff, p.ld_g, rows_valid, accW);
+            if (p.gS) {
+              if (p.accumulate) {
+                get_tile_f32(my_stage, lane, p.gS + goff, p.ld_g, rows_valid, t);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) accS[j] += t[j];
+              }
+              put_tile_f32(my_stage, lane, p.gS + goff, p.ld_g, rows_valid, accS);
+            }
+          } else if (row < p.M) {
+            const bool vec_g = (p.ld_g & 3) == 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int cq = col0 + 4 * j;
+              if (cq >= p.N) break;
+              const int nvalid = min(4, p.N - cq);
+              float* gw = p.gW + (long long)row * p.ld_g + cq;
+              float w4[4] = {accW[4 * j], accW[4 * j + 1], accW[4 * j + 2], accW[4 * j + 3]};
+              if (p.accumulate) { float o[4]; load4<float>(gw, o, nvalid, vec_g); for (int k = 0; k < 4; ++k) w4[k] += o[k]; }
+              store4<float>(gw, w4, nvalid, vec_g);
+              if (p.gS) {
+                float* gs = p.gS + (long long)row * p.ld_g + cq;
+                float s4[4] = {accS[4 * j], accS[4 * j + 1], accS[4 * j + 2], accS[4 * j + 3]};
+                if (p.accumulate) { float o[4]; load4<float>(gs, o, nvalid, vec_g); for (int k = 0; k < 4; ++k) s4[k] += o[k]; }
+                store4<float>(gs, s4, nvalid, vec_g);
+              }
+            }
+          }
+        }
+      } else {
       for (int z = zb; z < zb + zn; ++z) {
         mbar_wait(tfull_bar(as), aphase);
         tc_fence_after();
@@ -492,6 +584,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
           else mbar_arrive_remote(tempty_bar(as), 0);      // the leader's barrier
         }
         if (++as == AS) { as = 0; aphase ^= 1; }
+      }
       }
     }
   }
@@ -554,7 +647,7 @@ int make_tmap(CUtensorMap* tm, const TcOperand& op, int rows_mn, int K, int batc
   return VBNN_OK;
 }
 
-struct TcChoice { int bn, cg; };
+struct TcChoice { int bn, cg; };   // bn == 64: multi-sample dW with register accumulation
 int g_block_n_override = 0;
 int g_cg_override = 0;
 
@@ -628,6 +721,11 @@ TcChoice choose_cfg(const TcGemmArgs& g) {
   if (!c.bn) { const char* e = getenv("VBNN_TC_BN"); if (e) c.bn = atoi(e); }      // debugging knobs
   if (!c.cg) { const char* e = getenv("VBNN_TC_CG"); if (e) c.cg = atoi(e); }
   if ((c.bn == 128 || c.bn == 256) && (c.cg == 1 || c.cg == 2) && !(c.bn == 128 && c.cg == 2)) return c;
+  if (epi_z_accumulates(MODE) && g.batch > 1) {
+    static int z64 = -1;
+    if (z64 < 0) { const char* e = getenv("VBNN_TC_DW64"); z64 = e ? atoi(e) : 1; }
+    if (z64) return TcChoice{64, 1};
+  }
   const long long zmul = epi_z_accumulates(MODE) ? 1 : g.batch;
   auto cost = [&](int bn, int cg, double speed) {
     const long long work = (long long)ceil_div(g.M, BM * cg) * ceil_div(g.N, bn) * zmul;
@@ -642,6 +740,9 @@ TcChoice choose_cfg(const TcGemmArgs& g) {
 template <int MODE, bool AK, bool BKM>
 int launch_any(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
   const TcChoice c = choose_cfg<MODE>(g);
+  if constexpr (epi_z_accumulates(MODE)) {
+    if (c.bn == 64) return launch_cfg<MODE, 64, 1, AK, BKM>(g, p, st);
+  }
   if (c.cg == 2) return launch_cfg<MODE, 256, 2, AK, BKM>(g, p, st);
   if (c.bn == 256 && !epi_is_dual(MODE)) return launch_cfg<MODE, epi_is_dual(MODE) ? 128 : 256, 1, AK, BKM>(g, p, st);
   return launch_cfg<MODE, 128, 1, AK, BKM>(g, p, st);

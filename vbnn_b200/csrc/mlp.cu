@@ -211,7 +211,27 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
     p.step_ptr = m->ctx->d_step;
     if (L->eps_injected && Zrun == 1 && L->eps) p.noise = L->eps;      // parity mode: injected epsilon
     const int mode = lrt ? EPI_DW_LRT : EPI_DW;
-    if (m->bf16) {
+    static int split_env = -1;
+    if (split_env < 0) { const char* e = getenv("VBNN_DW_SPLIT"); split_env = e ? atoi(e) : 1; }
+    if (m->bf16 && lrt && split_env) {
+      // The two LRT parameter gradients are independent (g_mu = G^T X, g_s = H^T X^2): as two
+      // single-accumulator GEMMs each tile needs half the TMEM, so the accumulator is double-buffered
+      // and the epilogue of tile i hides behind the MMAs of tile i+1 (the dual kernel cannot).
+      TcGemmArgs g;
+      memset(&g, 0, sizeof(g));
+      g.M = L->O; g.N = L->I; g.K = N; g.batch = Zrun;
+      g.A1 = {(const bf16*)m->G[j], ldo, 0, zs_out};
+      g.B1 = {(const bf16*)m->act[j], ldi, 0, zs_in};
+      EpiParams p1 = p;
+      p1.gS = nullptr;
+      p1.noise = nullptr;
+      VB_TRY(tc_gemm(m->ctx, EPI_DW, g, p1));
+      g.A1 = {(const bf16*)m->H[j], ldo, 0, zs_out};
+      g.B1 = {(const bf16*)m->act2[j], ldi, 0, zs_in};
+      p1.gW = L->gS;                      // plain accumulate of H^T X^2 into gradSum
+      p1.scale = 1.f;
+      VB_TRY(tc_gemm(m->ctx, EPI_DW, g, p1));
+    } else if (m->bf16) {
       TcGemmArgs g;
       memset(&g, 0, sizeof(g));
       g.M = L->O; g.N = L->I; g.K = N; g.batch = Zrun;
