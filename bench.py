@@ -229,6 +229,16 @@ def main():
 
     N = w["N"]
     net, opt = build_net(w, ctx, N)
+    dp_mode = "single"
+    if world > 1:
+        dp_mode = os.environ.get("VBNN_DP", "peer")
+        if dp_mode == "peer":
+            def gather_bytes(blob):
+                t = torch.tensor(list(blob), dtype=torch.uint8, device=f"cuda:{local_rank}")
+                out = [torch.empty_like(t) for _ in range(world)]
+                dist.all_gather(out, t)
+                return [bytes(o.cpu().tolist()) for o in out]
+            net.enable_peer(gather_bytes)
     g = torch.Generator(device="cpu").manual_seed(3 + rank)
     nbuf = 2
     Xd = [torch.randn(N, w["sizes"][0], generator=g).cuda() for _ in range(nbuf)]
@@ -258,6 +268,7 @@ def main():
     ms = ev0.elapsed_time(ev1)
     launches = net.launch_count() - l0
     prof = ctx.profile_read() if w["precision"] == "bf16" else {}
+    phases = ctx.phase_read() if w["precision"] == "bf16" else {}
     ctx.profile(False)
     err_last = float(net._res.cpu()[0])
     if dist is not None:
@@ -315,13 +326,14 @@ def main():
                 warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16" if w["precision"] == "bf16" else "f32", data="synthetic",
                 config=dict(workload=w["desc"], sizes=w["sizes"], global_batch=N * world, per_gpu_batch=N, S=w["S"],
-                            reparam=w["reparam"], parallelism=f"dp{world}", output_layer="nn.Linear (mlp.lua:29)",
+                            reparam=w["reparam"], parallelism=f"dp{world}", dp_exchange=dp_mode, output_layer="nn.Linear (mlp.lua:29)",
                             l2="working set (parameters + optimizer state + activations) >> 126 MB L2; two "
                                "alternating input minibatches",
                             flops_per_sample=fps),
                 step_tflops=fps * N / (ms / args.steps / 1e3) / 1e12,
                 step_frac_of_peak=fps * N / (ms / args.steps / 1e3) / 1e12 / peaks["tflops"],
-                gpu_launches=launches, clocks=clocks, last_error=err_last)
+                gpu_launches=launches, clocks=clocks, last_error=err_last,
+                phases_ms_per_step={k: v[0] / args.steps for k, v in phases.items()})
     if e2e:
         line["e2e"] = e2e
     if roof:

@@ -119,6 +119,9 @@ int vbnn_ctx_synchronize(vbnn_ctx* ctx);
  * what bench.py's roofline object is computed from. */
 int vbnn_ctx_profile(vbnn_ctx* ctx, int enable);
 int vbnn_ctx_profile_read(vbnn_ctx* ctx, int cls, double* total_ms, long long* launches, double* flops);
+/* same switch: time between phase marks of the minibatch (1 start..params ready, 2 sample, 3 forward,
+ * 4 loss, 5 backward (per layer), 6 exchange + update, 7 finalise) */
+int vbnn_ctx_phase_read(vbnn_ctx* ctx, int id, double* total_ms, long long* count);
 int vbnn_ctx_set_step(vbnn_ctx* ctx, uint32_t step);   /* Philox "minibatch" counter */
 int vbnn_ctx_get_step(vbnn_ctx* ctx, uint32_t* step);
 
@@ -232,6 +235,23 @@ int vbnn_comm_unique_id(void* id128);                       /* 128-byte ncclUniq
 int vbnn_comm_init(vbnn_ctx* ctx, const void* id128, int rank, int nranks);
 int vbnn_comm_destroy(vbnn_ctx* ctx);
 int vbnn_comm_allreduce(vbnn_ctx* ctx, float* buf_dev, size_t count);
+
+/* Peer mode: the same exchange without any collective call, fused into the hot path over NVLink
+ * peer memory (CUDA IPC; one process per GPU of one box).  Rows [q*rpo, (q+1)*rpo) of every layer
+ * belong to rank q: the dW GEMM epilogue stores each gradient tile straight into its owner's
+ * receive slot (reduce-scatter), the owner's fused update sums the slots for its rows only, and
+ * the copy engines push the refreshed operands to every rank (all-gather) while backward
+ * continues.  Set-up: after vbnn_comm_init, every rank exports a blob (blob == NULL queries its
+ * size), the host all-gathers the blobs (rank order, blob_len bytes each) and every rank imports
+ * them.  vbnn_mlp_step / vbnn_mlp_submit_host then use the peer path. */
+int vbnn_mlp_peer_export(vbnn_mlp* mlp, void* blob, size_t capacity, size_t* blob_len);
+int vbnn_mlp_peer_import(vbnn_mlp* mlp, const void* blobs_all_ranks, size_t blob_len);
+int vbnn_mlp_peer_active(const vbnn_mlp* mlp);
+/* collective (host barrier before and after): refresh the fp32 state of rows owned by other ranks
+ * (Adam moments, and whatever training does not push) before get / checkpoint / clamp_to_map */
+int vbnn_mlp_sync_replicas(vbnn_mlp* mlp);
+/* shard of an O-row matrix owned by `rank`; returns rows per owner (a multiple of 32) */
+int vbnn_peer_shard(int O, int nranks, int rank, int* row0, int* rows);
 
 /* ---------------------------------------------------------------- self-test hooks -----
  * Raw GEMM entry used by tests/profiling to exercise the tcgen05 kernel in isolation:

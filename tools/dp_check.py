@@ -35,6 +35,13 @@ def main():
         dist.broadcast(t, 0)
         return bytes(t.cpu().tolist())
     ctx_dp.init_comm(rank, world, bcast)
+
+    def gather_bytes(blob):
+        t = torch.tensor(list(blob), dtype=torch.uint8, device=f"cuda:{lr}")
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [bytes(o.cpu().tolist()) for o in out]
+    use_peer = os.environ.get("VBNN_DP", "peer") == "peer"
     ok = True
     for reparam, precision, sizes, N, S in [("weight", "fp32", [64, 96, 80, 10], 64, 2),
                                            ("local", "fp32", [64, 96, 80, 10], 64, 2),
@@ -45,9 +52,16 @@ def main():
         T = torch.randint(1, sizes[-1] + 1, (N,), generator=g).float()
         n_loc = N // world
         net = build(ctx_dp, sizes, n_loc, S, reparam, precision)
+        if use_peer:
+            net.enable_peer(gather_bytes)
         ctx_dp.set_step(7)
+        dist.barrier()
         for it in range(3):
             net.train_step(X[rank * n_loc:(rank + 1) * n_loc].cuda(), T[rank * n_loc:(rank + 1) * n_loc].cuda())
+        if use_peer:
+            ctx_dp.synchronize(); dist.barrier()
+            net.sync_replicas()
+            dist.barrier()
         dp = [m.means.clone() for m in net.model[:-1]] + [net.model[-1].weight.clone()]
         dp_lv = [m.lvars.clone() for m in net.model[:-1]]
         # all ranks must hold identical parameters
@@ -66,12 +80,14 @@ def main():
             for a, b in zip(dp, sg):
                 e = float((a - b).norm() / b.norm())
                 ok &= e < tol
-                print(f"{reparam}/{precision}: rel err DP vs single = {e:.2e}")
+                print(f"{reparam}/{precision} ({'peer' if net.peer_active else 'nccl'}): rel err DP vs single = {e:.2e}")
             for a, m in zip(dp_lv, one.model[:-1]):
                 e = float((a - m.lvars).norm() / m.lvars.norm())
                 ok &= e < tol
             torch.cuda.set_stream(ctx_dp.stream)
+        ctx_dp.synchronize(); dist.barrier()          # nobody still writes into a peer's buffers
         del net
+        dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{lr}")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

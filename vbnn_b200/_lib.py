@@ -50,6 +50,7 @@ _PROTOS = {
     "vbnn_ctx_synchronize": (C.c_int, [_P]),
     "vbnn_ctx_profile": (C.c_int, [_P, C.c_int]),
     "vbnn_ctx_profile_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]),
+    "vbnn_ctx_phase_read": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vbnn_ctx_set_step": (C.c_int, [_P, C.c_uint32]),
     "vbnn_ctx_get_step": (C.c_int, [_P, C.POINTER(C.c_uint32)]),
     "vbnn_layer_create": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.POINTER(VbnnOpts), C.POINTER(_P)]),
@@ -94,6 +95,11 @@ _PROTOS = {
     "vbnn_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "vbnn_comm_destroy": (C.c_int, [_P]),
     "vbnn_comm_allreduce": (C.c_int, [_P, _P, C.c_size_t]),
+    "vbnn_mlp_peer_export": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "vbnn_mlp_peer_import": (C.c_int, [_P, _P, C.c_size_t]),
+    "vbnn_mlp_peer_active": (C.c_int, [_P]),
+    "vbnn_mlp_sync_replicas": (C.c_int, [_P]),
+    "vbnn_peer_shard": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vbnn_gemm_bf16": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int,
                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
                                  C.c_longlong]),

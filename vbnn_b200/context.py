@@ -50,6 +50,17 @@ class Context:
                 out[name] = (ms.value, n.value, fl.value)
         return out
 
+    def phase_read(self):
+        """{phase: (total_ms, count)} between the step's phase marks since profile(True)."""
+        names = {1: "wait_params", 2: "sample", 3: "forward", 4: "loss", 5: "backward", 6: "exchange_update", 7: "finalise"}
+        out = {}
+        for i, name in names.items():
+            ms, n = C.c_double(), C.c_longlong()
+            L.check(L.lib().vbnn_ctx_phase_read(self.handle, i, C.byref(ms), C.byref(n)))
+            if n.value:
+                out[name] = (ms.value, n.value)
+        return out
+
     def close(self):
         if self.handle:
             L.lib().vbnn_ctx_destroy(self.handle)

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateParams p) {
     for (int i = threadIdx.x; i < p.n_partials; i += blockDim.x) a += part[i];
     double r = block_sum(a, sh);
     if (threadIdx.x == 0) {
-      const long long W = (long long)p.O * p.I;
+      const long long W = p.W_total > 0 ? p.W_total : (long long)p.O * p.I;
       float vh = (float)(r / (double)W);
       s_var_hat = vh;
       if (blockIdx.x == 0) *p.var_hat_dev = vh;
@@ -207,6 +207,12 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateParams p) {
         for (int j = 0; j < nv; ++j) dst[e0 + j] = d[j];
     };
     load(p.mu, mu); load(p.lvar, lv); load(p.gW, gw); load(p.gS, gs);
+    for (int src = 1; src < p.n_src; ++src) {            // peer mode: sum the ranks' receive slots
+      float a[4], b[4];
+      load(p.gW + src * p.src_stride, a); load(p.gS + src * p.src_stride, b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { gw[j] += a[j]; gs[j] += b[j]; }
+    }
     load(p.m_mu, mm); load(p.v_mu, vm); load(p.m_var, mv); load(p.v_var, vv);
     float sd_old[4], musq[4], s2_new[4];
 #pragma unroll
@@ -261,8 +267,11 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateParams p) {
   }
   if (p.next_partials) {
     double r = block_sum((double)nxt, sh);
-    if (threadIdx.x == 0)
-      p.next_partials[(p.partials_pingpong ? (size_t)((t_now + 1) & 1) * kMaxPartials : 0) + blockIdx.x] = r;
+    if (threadIdx.x == 0) {
+      const size_t idx = (p.partials_pingpong ? (size_t)((t_now + 1) & 1) * kMaxPartials : 0) + p.part_off + blockIdx.x;
+      p.next_partials[idx] = r;
+      for (int q = 0; q < p.n_peer; ++q) p.peer_partials[q][idx] = r;
+    }
   }
   if (STATS) {
     // sums in slots 0..9, min/max in 11..14
@@ -346,6 +355,23 @@ __global__ void __launch_bounds__(kThreads) k_sgd(float* x, const float* g, long
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     float v = x[e] - lr * g[e];
+    x[e] = v;
+    if (xb) {
+      long long o = e / I;
+      int i = (int)(e - o * I);
+      xb[o * ld + i] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// peer mode: the gradient is the sum of the ranks' receive slots
+__global__ void __launch_bounds__(kThreads) k_sgd_slots(float* x, const float* g, int n_src, long long src_stride,
+                                                        long long n, float lr, bf16* xb, int I, int ld) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
+       e += (long long)gridDim.x * blockDim.x) {
+    float gs = 0.f;
+    for (int s = 0; s < n_src; ++s) gs += g[e + s * src_stride];
+    float v = x[e] - lr * gs;
     x[e] = v;
     if (xb) {
       long long o = e / I;
@@ -612,7 +638,7 @@ int launch_prior_finalize(const double* partials, int n_partials, long long W, f
 }
 
 int launch_update(const UpdateParams& p, int* grid_out, cudaStream_t st) {
-  const int grid = update_grid(p.O, p.I);
+  const int grid = p.grid_override > 0 ? p.grid_override : update_grid(p.O, p.I);
   const bool vec = (p.I & 3) == 0;
   const bool stats = p.stat_partials != nullptr;
   if (vec && stats) k_update<true, true><<<grid, kThreads, 0, st>>>(p);
@@ -649,6 +675,14 @@ int launch_sgd(float* x, const float* g, long long n, float lr, bf16* x_bf16, in
                cudaStream_t st) {
   if (n <= 0) return VBNN_OK;
   k_sgd<<<grid_for(n), kThreads, 0, st>>>(x, g, n, lr, x_bf16, I, ld_bf16);
+  VB_CUDA(cudaGetLastError());
+  return VBNN_OK;
+}
+
+int launch_sgd_slots(float* x, const float* g, int n_src, long long src_stride, long long n, float lr,
+                     bf16* x_bf16, int I, int ld_bf16, cudaStream_t st) {
+  if (n <= 0) return VBNN_OK;
+  k_sgd_slots<<<grid_for(n), kThreads, 0, st>>>(x, g, n_src, src_stride, n, lr, x_bf16, I, ld_bf16);
   VB_CUDA(cudaGetLastError());
   return VBNN_OK;
 }

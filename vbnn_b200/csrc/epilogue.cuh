@@ -55,7 +55,19 @@ struct EpiParams {
   float* gW; float* gS; int ld_g;
   float scale;               // accGradParameters' scale
   int accumulate;            // 0: first z overwrites (saves the memset), 1: always +=
+  // peer mode: rows [q*scatter_rows, (q+1)*scatter_rows) go to rank q's receive slot (pointers are
+  // pre-biased so that row * ld_g + col indexes them like gW / gS); 0 = plain local gW / gS
+  int scatter_rows;
+  float* gW_peer[8]; float* gS_peer[8];
 };
+
+// destination of a dW tile whose rows all share one owner (32-row warp chunks: scatter_rows % 32 == 0)
+__device__ __forceinline__ void dw_dest(const EpiParams& p, int row, float*& gW, float*& gS) {
+  if (p.scatter_rows == 0) { gW = p.gW; gS = p.gS; return; }
+  const int q = row / p.scatter_rows;
+  gW = p.gW_peer[q];
+  gS = p.gS_peer[q];
+}
 
 template <typename AT> struct Vec4;
 template <> struct Vec4<float> {
@@ -208,14 +220,16 @@ __device__ __forceinline__ void epi_quad(const EpiParams& p, const PhiloxStream&
     const bool vec_g = (p.ld_g & 3) == 0;
     long long goff = (long long)row * p.ld_g + col;
     const bool acc = p.accumulate || z > 0;
+    float *gWd, *gSd;
+    dw_dest(p, row, gWd, gSd);
     float w[4] = {0.f, 0.f, 0.f, 0.f};
-    if (acc) load4<float>(p.gW + goff, w, nvalid, vec_g);
+    if (acc) load4<float>(gWd + goff, w, nvalid, vec_g);
 #pragma unroll
     for (int j = 0; j < 4; ++j) w[j] += p.scale * a1[j];
-    store4<float>(p.gW + goff, w, nvalid, vec_g);
+    store4<float>(gWd + goff, w, nvalid, vec_g);
     if (p.gS) {
       float s[4] = {0.f, 0.f, 0.f, 0.f};
-      if (acc) load4<float>(p.gS + goff, s, nvalid, vec_g);
+      if (acc) load4<float>(gSd + goff, s, nvalid, vec_g);
       if constexpr (MODE == EPI_DW) {
         float e[4];
         if (p.noise) {
@@ -232,7 +246,7 @@ __device__ __forceinline__ void epi_quad(const EpiParams& p, const PhiloxStream&
 #pragma unroll
         for (int j = 0; j < 4; ++j) s[j] += a2[j];
       }
-      store4<float>(p.gS + goff, s, nvalid, vec_g);
+      store4<float>(gSd + goff, s, nvalid, vec_g);
     }
   }
 }

@@ -130,6 +130,9 @@ inline bool epi_can_stage(int mode, const EpiParams& p) {
   if (!ok_act(p.out_act, p.ld_act) || !ok_act(p.out_act2, p.ld_act) || !ok_act(p.r_out, p.ld_act) || (p.zs_act % 8) != 0) return false;
   if (!ok_act(p.xprev, p.ld_x) || !ok_act(p.rprev, p.ld_x) || (p.zs_x % 8) != 0) return false;
   if (!ok_f32(p.gW, p.ld_g) || !ok_f32(p.gS, p.ld_g)) return false;
+  if (p.scatter_rows)
+    for (int q = 0; q < 8; ++q)
+      if (!ok_f32(p.gW_peer[q], p.ld_g) || !ok_f32(p.gS_peer[q], p.ld_g)) return false;
   if (p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) % 16) != 0) return false;
   (void)mode;
   return true;
@@ -229,18 +232,20 @@ __device__ __forceinline__ void epi_chunk_staged(const EpiParams& p, const Philo
   } else if constexpr (MODE == EPI_DW || MODE == EPI_DW_LRT) {
     const long long goff = (long long)row0 * p.ld_g + col0;
     const bool acc = p.accumulate || z > 0;
+    float *gWd, *gSd;
+    dw_dest(p, row0, gWd, gSd);
     float t[32];
     if (acc) {
-      get_tile_f32(stage, lane, p.gW + goff, p.ld_g, rows_valid, t);
+      get_tile_f32(stage, lane, gWd + goff, p.ld_g, rows_valid, t);
 #pragma unroll
       for (int j = 0; j < 32; ++j) t[j] += p.scale * v1[j];
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j) t[j] = p.scale * v1[j];
     }
-    put_tile_f32(stage, lane, p.gW + goff, p.ld_g, rows_valid, t);
+    put_tile_f32(stage, lane, gWd + goff, p.ld_g, rows_valid, t);
     if (p.gS) {
-      if (acc) get_tile_f32(stage, lane, p.gS + goff, p.ld_g, rows_valid, t);
+      if (acc) get_tile_f32(stage, lane, gSd + goff, p.ld_g, rows_valid, t);
       else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] = 0.f;
@@ -260,7 +265,7 @@ __device__ __forceinline__ void epi_chunk_staged(const EpiParams& p, const Philo
 #pragma unroll
         for (int j = 0; j < 32; ++j) t[j] += v2[j];
       }
-      put_tile_f32(stage, lane, p.gS + goff, p.ld_g, rows_valid, t);
+      put_tile_f32(stage, lane, gSd + goff, p.ld_g, rows_valid, t);
     }
   }
 }

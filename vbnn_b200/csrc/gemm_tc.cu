@@ -517,22 +517,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         if (col0 < sh.N) {
           const int row0 = m0 + q * 32;
           const long long goff = (long long)row0 * p.ld_g + col0;
+          float *gWd, *gSd;
+          dw_dest(p, row0, gWd, gSd);
           if (sh.staged && col0 + 32 <= sh.N) {
             const int rows_valid = min(32, p.M - row0);
             float t[32];
             if (p.accumulate) {
-              get_tile_f32(my_stage, lane, p.gW + goff, p.ld_g, rows_valid, t);
+              get_tile_f32(my_stage, lane, gWd + goff, p.ld_g, rows_valid, t);
 #pragma unroll
               for (int j = 0; j < 32; ++j) accW[j] += t[j];
             }
-            put_tile_f32(my_stage, lane, p.gW + goff, p.ld_g, rows_valid, accW);
+            put_tile_f32(my_stage, lane, gWd + goff, p.ld_g, rows_valid, accW);
             if (p.gS) {
               if (p.accumulate) {
-                get_tile_f32(my_stage, lane, p.gS + goff, p.ld_g, rows_valid, t);
+                get_tile_f32(my_stage, lane, gSd + goff, p.ld_g, rows_valid, t);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) accS[j] += t[j];
               }
-              put_tile_f32(my_stage, lane, p.gS + goff, p.ld_g, rows_valid, accS);
+              put_tile_f32(my_stage, lane, gSd + goff, p.ld_g, rows_valid, accS);
             }
           } else if (row < p.M) {
             const bool vec_g = (p.ld_g & 3) == 0;
@@ -541,12 +543,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               const int cq = col0 + 4 * j;
               if (cq >= p.N) break;
               const int nvalid = min(4, p.N - cq);
-              float* gw = p.gW + (long long)row * p.ld_g + cq;
+              float* gw = gWd + (long long)row * p.ld_g + cq;
               float w4[4] = {accW[4 * j], accW[4 * j + 1], accW[4 * j + 2], accW[4 * j + 3]};
               if (p.accumulate) { float o[4]; load4<float>(gw, o, nvalid, vec_g); for (int k = 0; k < 4; ++k) w4[k] += o[k]; }
               store4<float>(gw, w4, nvalid, vec_g);
               if (p.gS) {
-                float* gs = p.gS + (long long)row * p.ld_g + cq;
+                float* gs = gSd + (long long)row * p.ld_g + cq;
                 float s4[4] = {accS[4 * j], accS[4 * j + 1], accS[4 * j + 2], accS[4 * j + 3]};
                 if (p.accumulate) { float o[4]; load4<float>(gs, o, nvalid, vec_g); for (int k = 0; k < 4; ++k) s4[k] += o[k]; }
                 store4<float>(gs, s4, nvalid, vec_g);
@@ -720,7 +722,7 @@ TcChoice choose_cfg(const TcGemmArgs& g) {
   TcChoice c{g_block_n_override, g_cg_override};
   if (!c.bn) { const char* e = getenv("VBNN_TC_BN"); if (e) c.bn = atoi(e); }      // debugging knobs
   if (!c.cg) { const char* e = getenv("VBNN_TC_CG"); if (e) c.cg = atoi(e); }
-  if ((c.bn == 128 || c.bn == 256) && (c.cg == 1 || c.cg == 2) && !(c.bn == 128 && c.cg == 2)) return c;
+  if ((c.bn == 128 || c.bn == 256) && (c.cg == 1 || c.cg == 2) && !(c.bn == 128 && c.cg == 2 && !epi_is_dual(MODE))) return c;
   if (epi_z_accumulates(MODE) && g.batch > 1) {
     static int z64 = -1;
     if (z64 < 0) { const char* e = getenv("VBNN_TC_DW64"); z64 = e ? atoi(e) : 1; }
@@ -742,6 +744,10 @@ int launch_any(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
   const TcChoice c = choose_cfg<MODE>(g);
   if constexpr (epi_z_accumulates(MODE)) {
     if (c.bn == 64) return launch_cfg<MODE, 64, 1, AK, BKM>(g, p, st);
+  }
+  if constexpr (epi_is_dual(MODE)) {
+    // 256 x 128 pair tile: two accumulators use 256 TMEM columns, so the accumulator is double-buffered
+    if (c.cg == 2 && c.bn == 128) return launch_cfg<MODE, 128, 2, AK, BKM>(g, p, st);
   }
   if (c.cg == 2) return launch_cfg<MODE, 256, 2, AK, BKM>(g, p, st);
   if (c.bn == 256 && !epi_is_dual(MODE)) return launch_cfg<MODE, epi_is_dual(MODE) ? 128 : 256, 1, AK, BKM>(g, p, st);

@@ -56,6 +56,12 @@ struct UpdateParams {
   double* stat_partials;                // nullable [grid x kStatSlots]
   double* next_partials;                // nullable [grid]: sum(exp(lvar_new) + mu_new^2) per block, i.e.
                                         // the compute_prior partials of the NEXT update (saves a read pass)
+  // ---- peer mode (row shard of a layer; all pointers above are pre-offset to the shard, O = its rows) ----
+  long long W_total;                    // weights of the WHOLE layer (var_hat denominator); 0 -> O * I
+  int n_src; long long src_stride;      // > 0: gW / gS are sums of n_src receive slots, src_stride floats apart
+  int grid_override;                    // > 0: blocks of this launch
+  int part_off;                         // this launch's first index in the next_partials array
+  int n_peer; double* peer_partials[7]; // next_partials mirrored into the other ranks' arrays (peer stores)
 };
 int launch_update(const UpdateParams& p, int* grid_out, cudaStream_t st);
 
@@ -72,6 +78,9 @@ int launch_calc_lc(const float* var_src, int var_kind /*0 lvar, 1 stdv*/, const 
 // x -= lr * g  (optim.sgd, VBLinear.lua:125-128, mlp.lua:120-123) + optional bf16 operand copy
 int launch_sgd(float* x, const float* g, long long n, float lr, bf16* x_bf16, int I, int ld_bf16,
                cudaStream_t st);
+// peer mode: g = sum of n_src receive slots src_stride floats apart
+int launch_sgd_slots(float* x, const float* g, int n_src, long long src_stride, long long n, float lr,
+                     bf16* x_bf16, int I, int ld_bf16, cudaStream_t st);
 
 // LogSoftMax + ClassNLLCriterion forward/backward + accuracy (mlp.lua:30-32,78-82; utils.lua:11-27)
 struct LossParams {

@@ -83,7 +83,7 @@ int layer_compute_prior_internal(vbnn_layer* L) {
 int layer_refresh_prior_partials(vbnn_layer* L) {
   if (L->kind != VBNN_KIND_VB) return VBNN_OK;
   VB_TRY(launch_prior_partials_pp(L->means, L->lvars, (long long)L->O * L->I, L->prior_partials, L->t_dev,
-                                  update_grid(L->O, L->I), L->ctx->stream));
+                                  L->n_part, L->ctx->stream));
   L->ctx->launches++;
   return VBNN_OK;
 }
@@ -100,6 +100,7 @@ int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts
   L->id = id >= 0 ? id : 0x1000 + ctx->next_layer_id++;
   L->ldI = round_up(I, 8); L->ldO = round_up(O, 8);
   L->S_alloc = S_alloc < 1 ? 1 : S_alloc;
+  L->n_part = update_grid(O, I);
   cudaStream_t st = ctx->stream;
   const size_t W = (size_t)O * I;
   const bool vb = kind == VBNN_KIND_VB, b16 = is_bf16(L), lrt = is_lrt(L);
@@ -208,7 +209,7 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
   u.stdv = L->stdv; u.mu_sqe = L->mu_sqe;
   u.mu_bf16 = L->mu_bf16; u.s2_bf16 = L->s2_bf16; u.ld_bf16 = L->ldI; u.s2_f32 = L->s2_f32;
   u.O = L->O; u.I = L->I;
-  u.partials = L->prior_partials; u.n_partials = update_grid(L->O, L->I);
+  u.partials = L->prior_partials; u.n_partials = L->n_part;
   u.next_partials = L->prior_partials; u.partials_pingpong = 1;
   u.var_hat_dev = L->var_hat_dev; u.t_dev = L->t_dev;
   u.B = L->opts.B; u.S = (float)L->opts.S;
@@ -279,13 +280,33 @@ int tc_gemm(vbnn_ctx* c, int mode, const TcGemmArgs& g, const EpiParams& p) {
   int rc = gemm_tc_launch(mode, g, p, c->stream, &c->launches);
   VB_CUDA(cudaEventRecord(r.b, c->stream));
   c->prof_recs.push_back(r);
-  if (c->prof_recs.size() >= 4096) VB_TRY(prof_collect(c));
+  if (c->prof_recs.size() + c->marks.size() >= 4096) VB_TRY(prof_collect(c));
   return rc;
 }
 
+int prof_mark(vbnn_ctx* c, int id) {
+  if (!c->profiling) return VBNN_OK;
+  cudaEvent_t e;
+  if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); }
+  else VB_CUDA(cudaEventCreate(&e));
+  VB_CUDA(cudaEventRecord(e, c->stream));
+  c->marks.push_back({e, id});
+  return VBNN_OK;
+}
+
 int prof_collect(vbnn_ctx* c) {
-  if (c->prof_recs.empty()) return VBNN_OK;
+  if (c->prof_recs.empty() && c->marks.empty()) return VBNN_OK;
   VB_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t i = 0; i < c->marks.size(); ++i) {
+    const int id = c->marks[i].id & 15;
+    if (i > 0 && id != 0) {
+      float ms = 0.f;
+      VB_CUDA(cudaEventElapsedTime(&ms, c->marks[i - 1].e, c->marks[i].e));
+      c->phase_ms[id] += ms; c->phase_n[id] += 1;
+    }
+  }
+  for (auto& mk : c->marks) c->prof_pool.push_back(mk.e);
+  c->marks.clear();
   for (auto& r : c->prof_recs) {
     float ms = 0.f;
     VB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b));
@@ -376,6 +397,7 @@ extern "C" int vbnn_ctx_profile(vbnn_ctx* c, int enable) {
   VB_TRY(prof_collect(c));
   c->profiling = enable != 0;
   if (enable) for (int i = 0; i < 8; ++i) { c->prof_ms[i] = 0; c->prof_flops[i] = 0; c->prof_n[i] = 0; }
+  if (enable) for (int i = 0; i < 16; ++i) { c->phase_ms[i] = 0; c->phase_n[i] = 0; }
   return VBNN_OK;
 }
 extern "C" int vbnn_ctx_profile_read(vbnn_ctx* c, int cls, double* total_ms, long long* launches, double* flops) {
@@ -384,6 +406,13 @@ extern "C" int vbnn_ctx_profile_read(vbnn_ctx* c, int cls, double* total_ms, lon
   if (total_ms) *total_ms = c->prof_ms[cls];
   if (launches) *launches = c->prof_n[cls];
   if (flops) *flops = c->prof_flops[cls];
+  return VBNN_OK;
+}
+extern "C" int vbnn_ctx_phase_read(vbnn_ctx* c, int id, double* total_ms, long long* count) {
+  VB_CHECK(c && id >= 0 && id < 16, VBNN_E_INVALID, "vbnn_ctx_phase_read: bad argument");
+  VB_TRY(prof_collect(c));
+  if (total_ms) *total_ms = c->phase_ms[id];
+  if (count) *count = c->phase_n[id];
   return VBNN_OK;
 }
 extern "C" int vbnn_ctx_set_step(vbnn_ctx* c, uint32_t step) {
@@ -699,6 +728,13 @@ extern "C" int vbnn_layer_get(vbnn_layer* L, int which, float* dst) {
   cudaStream_t st = L->ctx->stream;
   float* p; size_t n;
   VB_TRY(buf_lookup(L, which, &p, &n));
+  if (L->shard_stale && *L->shard_stale) {
+    const bool sharded = which == VBNN_BUF_MEANS || which == VBNN_BUF_LVARS || which == VBNN_BUF_ADAM_M_MU ||
+                         which == VBNN_BUF_ADAM_V_MU || which == VBNN_BUF_ADAM_M_VAR || which == VBNN_BUF_ADAM_V_VAR ||
+                         (which == VBNN_BUF_WEIGHT && L->kind == VBNN_KIND_LINEAR);
+    VB_CHECK(!sharded, VBNN_E_STATE,
+             "peer mode: rows owned by other ranks are out of date; call vbnn_mlp_sync_replicas on every rank first");
+  }
   if (which == VBNN_BUF_WEIGHT && !p && L->w_bf16) {
     // bf16 precision keeps the sampled weights only as tensor-core operands: widen on the host
     std::vector<uint16_t> tmp((size_t)L->O * L->ldI);

@@ -157,7 +157,7 @@ int loss_all(vbnn_mlp* m, int N, int Zrun, bool backward, float* logp_out, float
 
 // model:backward for layer j (mlp.lua:79): updateGradInput (skipped for the first layer, whose
 // gradInput nobody reads) + accGradParameters.
-int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumulate) {
+int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumulate, bool scatter = false) {
   vbnn_layer* L = m->layers[j];
   const bool lrt = layer_lrt(L);
   const int ldi = m->ld[j], ldo = m->ld[j + 1];
@@ -210,9 +210,10 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
     p.ps = layer_stream(L, kStreamEps, sample0);
     p.step_ptr = m->ctx->d_step;
     if (L->eps_injected && Zrun == 1 && L->eps) p.noise = L->eps;      // parity mode: injected epsilon
+    if (scatter) peer_scatter(m, j, p);                                // reduce-scatter fused into the epilogue
     const int mode = lrt ? EPI_DW_LRT : EPI_DW;
     static int split_env = -1;
-    if (split_env < 0) { const char* e = getenv("VBNN_DW_SPLIT"); split_env = e ? atoi(e) : 1; }
+    if (split_env < 0) { const char* e = getenv("VBNN_DW_SPLIT"); split_env = e ? atoi(e) : 0; }
     if (m->bf16 && lrt && split_env) {
       // The two LRT parameter gradients are independent (g_mu = G^T X, g_s = H^T X^2): as two
       // single-accumulator GEMMs each tile needs half the TMEM, so the accumulator is double-buffered
@@ -263,14 +264,21 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
 
 // reduce_overlap: data-parallel step -- the allreduce of layer j's {gW, gS, gb} slice starts on the
 // communication stream as soon as its dW is done and overlaps the backward of the layers below.
-int run_samples(vbnn_mlp* m, int N, int Zrun, int sample0, int accumulate, bool backward, bool reduce_overlap = false) {
+int run_samples(vbnn_mlp* m, int N, int Zrun, int sample0, int accumulate, bool backward, bool reduce_overlap = false,
+                bool peer = false) {
   const int Lc = nlayers(m);
   vbnn_ctx* c = m->ctx;
   for (int j = 0; j < Lc; ++j) VB_TRY(forward_layer(m, j, N, Zrun, sample0, false));
+  VB_TRY(prof_mark(c, 3));
   VB_TRY(loss_all(m, N, Zrun, backward, nullptr, m->result_acc));
+  VB_TRY(prof_mark(c, 4));
   if (backward)
     for (int j = Lc - 1; j >= 0; --j) {
-      VB_TRY(backward_layer(m, j, N, Zrun, sample0, accumulate));
+      VB_TRY(backward_layer(m, j, N, Zrun, sample0, accumulate, peer));
+      VB_TRY(prof_mark(c, 5));
+      // peer mode: signal, then the owner update + all-gather of layer j run on the side stream while
+      // this stream continues with the layers below
+      if (peer) VB_TRY(peer_after_dw(m, j));
       if (reduce_overlap) {
         VB_CUDA(cudaEventRecord(m->ev_bwd[j], c->stream));
         VB_CUDA(cudaStreamWaitEvent(c->comm_stream, m->ev_bwd[j], 0));
@@ -306,9 +314,26 @@ int update_all(vbnn_mlp* m, bool wait_reduce = false) {
 // everything of one minibatch after input staging: main.lua:28-40
 int step_body(vbnn_mlp* m, int N) {
   cudaStream_t st = m->ctx->stream;
+  VB_TRY(prof_mark(m->ctx, 0));
   VB_CUDA(cudaMemsetAsync(m->result_acc, 0, (size_t)2 * m->Z * 4, st));
   for (vbnn_layer* L : m->layers) VB_CUDA(cudaMemsetAsync(L->gb, 0, (size_t)L->O * 4, st));   // main.lua:28
+  if (m->peer && m->peer->active) {
+    // data parallel over NVLink peer memory (peer.cu): no collective call anywhere in the step
+    VB_TRY(peer_check(m));
+    VB_TRY(peer_wait_params(m));                     // last step's operands from every owner have landed
+    VB_TRY(prof_mark(m->ctx, 1));
+    VB_TRY(sample_all(m, 0, m->Z));
+    VB_TRY(prof_mark(m->ctx, 2));
+    VB_TRY(run_samples(m, N, m->Z, 0, 0, true, false, true));
+    VB_TRY(launch_finalize_result(m->result_acc, m->Z, N, m->result, st));
+    VB_TRY(launch_bump(m->ctx->d_step, m->t_list_dev, 0, st));    // the layers' t counters advance on the side stream
+    m->ctx->launches += 2;
+    VB_TRY(prof_mark(m->ctx, 7));
+    return VBNN_OK;
+  }
+  VB_TRY(prof_mark(m->ctx, 1));
   VB_TRY(sample_all(m, 0, m->Z));                                                              // :33
+  VB_TRY(prof_mark(m->ctx, 2));
   const bool dp = m->ctx->nranks > 1;
   static int ov_env = -1;
   if (ov_env < 0) { const char* e = getenv("VBNN_DP_OVERLAP"); ov_env = e ? atoi(e) : 1; }
@@ -316,9 +341,11 @@ int step_body(vbnn_mlp* m, int N) {
   VB_TRY(run_samples(m, N, m->Z, 0, /*accumulate=*/0, true, overlap));                         // :34
   if (dp && !overlap) VB_TRY(comm_allreduce_internal(m->ctx, m->grad_arena, m->grad_count, st));
   VB_TRY(update_all(m, overlap));                                                              // :40
+  VB_TRY(prof_mark(m->ctx, 6));
   VB_TRY(launch_finalize_result(m->result_acc, m->Z, N, m->result, st));                       // :38-39
   VB_TRY(launch_bump(m->ctx->d_step, m->t_list_dev, m->n_t, st));
   m->ctx->launches += 2;
+  VB_TRY(prof_mark(m->ctx, 7));
   return VBNN_OK;
 }
 
@@ -454,6 +481,7 @@ extern "C" int vbnn_mlp_destroy(vbnn_mlp* m) {
   cudaStreamSynchronize(m->ctx->stream);
   cudaStreamSynchronize(m->ctx->copy_stream);
   if (m->graph) cudaGraphExecDestroy(m->graph);
+  peer_destroy(m);
   for (cudaEvent_t e : m->ev_bwd) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_red) cudaEventDestroy(e);
   for (vbnn_layer* L : m->layers) vbnn_layer_destroy(L);
@@ -553,6 +581,8 @@ extern "C" int vbnn_mlp_run(vbnn_mlp* m, const float* X, const float* T, int N, 
 
 extern "C" int vbnn_mlp_update(vbnn_mlp* m) {
   VB_CHECK(m, VBNN_E_INVALID, "null mlp");
+  VB_CHECK(!(m->peer && m->peer->active), VBNN_E_UNSUPPORTED,
+           "peer mode drives the whole minibatch through vbnn_mlp_step / vbnn_mlp_submit_host");
   if (m->ctx->nranks > 1)
     VB_TRY(comm_allreduce_internal(m->ctx, m->grad_arena, m->grad_count, m->ctx->stream));
   VB_TRY(update_all(m));
@@ -631,6 +661,7 @@ extern "C" int vbnn_mlp_collect(vbnn_mlp* m, float* err_host, float* acc_host) {
   VB_CHECK(m->inflight > 0, VBNN_E_STATE, "vbnn_mlp_collect: nothing in flight");
   vbnn_mlp::Slot& sl = m->slots[m->collect_idx & 1];
   VB_CUDA(cudaEventSynchronize(sl.done));
+  VB_TRY(peer_check(m));
   if (err_host) *err_host = sl.h_result[0];
   if (acc_host) *acc_host = sl.h_result[1];
   sl.busy = false;
@@ -652,6 +683,11 @@ extern "C" int vbnn_mlp_test(vbnn_mlp* m, const float* X, const float* T, int N,
   cudaStream_t st = c->stream;
   VB_TRY(stage_input(m, X, T, N));
   VB_CUDA(cudaMemsetAsync(m->result_acc, 0, (size_t)2 * m->Z * 4, st));
+  if (m->peer && m->peer->active) {
+    VB_CHECK(n_samples > 0 || !m->peer->stale, VBNN_E_STATE,
+             "vbnn_mlp_test(quicktest) in peer mode: call vbnn_mlp_sync_replicas on every rank first");
+    VB_TRY(peer_wait_params(m));
+  }
   const int Lc = nlayers(m);
   int total = 0;
   if (n_samples == 0) {

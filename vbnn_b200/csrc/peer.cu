@@ -1,0 +1,501 @@
+// peer.cu -- data-parallel gradient exchange fused into the hot path over NVLink peer memory
+// (new functionality: the reference is single-GPU).
+//
+// One process per GPU; every rank maps the others' buffers with CUDA IPC.  Per layer j and step:
+//
+//   reduce-scatter  fused into the dW GEMM: rows [q*rpo, (q+1)*rpo) of gradWeight / gradSum belong
+//                   to rank q, and the tcgen05 epilogue stores each finished tile straight into
+//                   rank q's receive slot for this rank (posted stores over NVLink, no staging
+//                   buffer, no separate collective kernel)                    -> peer_scatter()
+//   owner update    rank q's fused KL + Adam kernel sums the G slots of its shard while it reads
+//                   them; the update costs 1/G of the replicated one         -> peer_after_dw()
+//   all-gather      the refreshed operands of the shard (bf16 mu / sigma^2, or fp32 mu / log
+//                   sigma^2 for weight sampling) are pushed to every rank by the copy engines on a
+//                   side stream while the SMs continue with the backward pass of the layers below
+//
+// Ordering uses per-layer flags in peer memory (release/acquire at system scope): grad_ready[j][r]
+// is set on every rank by rank r once its dW tile stores and gradBias of layer j are out;
+// param_ready[j][q] is set on every rank by owner q once its pushes of layer j have completed.
+// Counters are per stream (mseq: main, sseq: side), so nothing races with the host or a graph.
+// Every wait is bounded: a rank that does not show up sets an error word instead of hanging.
+#include <cuda.h>
+#include <string.h>
+
+#include "state.h"
+
+namespace vbnn {
+
+namespace {
+
+constexpr uint32_t kBlobMagic = 0x56424E50u;   // "VBNP"
+constexpr int kBufsPerLayer = 12;
+constexpr unsigned long long kWaitTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
+
+struct BlobHeader { uint32_t magic, rank, nranks, n_entries; };
+struct BlobEntry { cudaIpcMemHandle_t handle; uint64_t offset, bytes; };
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ device side -----------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t need, int* err) {
+  if (ld_acquire_sys(flag) >= need) return;
+  const unsigned long long t0 = globaltimer_ns();
+  while (ld_acquire_sys(flag) < need) {
+    __nanosleep(200);
+    if (globaltimer_ns() - t0 > kWaitTimeoutNs) { *err = 1; return; }
+  }
+}
+
+// main stream, before the first forward GEMM of a step: every owner's operands of the previous
+// step have landed in this rank's buffers.  ready: [L][G]; seq: [2L], mseq_j = seq[2j].
+__global__ void k_wait_params(const uint32_t* ready, const uint32_t* seq, int L, int G, int* err) {
+  for (int t = threadIdx.x; t < L * G; t += blockDim.x) spin_until(ready + t, seq[2 * (t / G)], err);
+}
+
+struct SignalGrad {
+  const float* gb; int O;          // this rank's gradBias of the layer
+  float* gb_dst[kMaxPeers];        // rank q's gradBias slot for this rank
+  uint32_t* ready_dst[kMaxPeers];  // rank q's grad_ready[j][me]
+  uint32_t* mseq;
+  int G;
+};
+// main stream, after the dW GEMM + gradBias column sums of layer j
+__global__ void k_signal_grad(SignalGrad s) {
+  const uint32_t v = *s.mseq + 1u;
+  for (int q = 0; q < s.G; ++q)
+    for (int i = threadIdx.x; i < s.O; i += blockDim.x) s.gb_dst[q][i] = s.gb[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < s.G) st_release_sys(s.ready_dst[threadIdx.x], v);
+  if (threadIdx.x == 0) *s.mseq = v;
+}
+
+// side stream: every rank's gradient tiles of layer j have landed in this rank's receive slots
+__global__ void k_wait_grad(const uint32_t* ready /*[G]*/, const uint32_t* sseq, int G, int* err) {
+  if (threadIdx.x < G) spin_until(ready + threadIdx.x, *sseq + 1u, err);
+}
+
+struct SignalParam {
+  uint32_t* ready_dst[kMaxPeers];  // rank q's param_ready[j][me]
+  uint32_t* sseq;
+  int* t_dev;                      // the layer's optimiser step counter
+  int G;
+};
+// side stream, after the shard update and its copy-engine pushes
+__global__ void k_signal_param(SignalParam s) {
+  const uint32_t v = *s.sseq + 1u;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < s.G) st_release_sys(s.ready_dst[threadIdx.x], v);
+  if (threadIdx.x == 0) { *s.sseq = v; if (s.t_dev) *s.t_dev += 1; }
+}
+
+// ------------------------------------------------------------------ host helpers ----------
+typedef CUresult (*PFN_getRange)(CUdeviceptr*, size_t*, CUdeviceptr);
+PFN_getRange get_range_fn() {
+  static PFN_getRange fn = nullptr;
+  static bool tried = false;
+  if (tried) return fn;
+  tried = true;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+      qr == cudaDriverEntryPointSuccess)
+    fn = reinterpret_cast<PFN_getRange>(p);
+  return fn;
+}
+
+int make_entry(const void* ptr, size_t bytes, BlobEntry* e) {
+  memset(e, 0, sizeof(*e));
+  if (!ptr || !bytes) return VBNN_OK;
+  char* base = (char*)ptr;
+  if (PFN_getRange fn = get_range_fn()) {
+    CUdeviceptr b = 0; size_t sz = 0;
+    if (fn(&b, &sz, (CUdeviceptr)ptr) == CUDA_SUCCESS && b) base = (char*)b;
+  }
+  VB_CUDA(cudaIpcGetMemHandle(&e->handle, base));
+  e->offset = (uint64_t)((const char*)ptr - base);
+  e->bytes = bytes;
+  return VBNN_OK;
+}
+
+PeerBuf* layer_bufs(PeerLayer& pl, int k) {
+  PeerBuf* t[kBufsPerLayer] = {&pl.means, &pl.lvars, &pl.s2_f32, &pl.mu_bf16, &pl.s2_bf16, &pl.weight,
+                               &pl.w_bf16, &pl.partials, &pl.m_mu, &pl.v_mu, &pl.m_var, &pl.v_var};
+  return t[k];
+}
+void local_bufs(const vbnn_layer* L, const void* (&ptr)[kBufsPerLayer], size_t (&bytes)[kBufsPerLayer]) {
+  const size_t W = (size_t)L->O * L->I, Wb = (size_t)L->O * L->ldI;
+  const bool vb = L->kind == VBNN_KIND_VB;
+  const void* p[kBufsPerLayer] = {L->means, L->lvars, L->s2_f32, L->mu_bf16, L->s2_bf16,
+                                  vb ? nullptr : L->weight, vb ? nullptr : L->w_bf16, L->prior_partials,
+                                  L->m_mu, L->v_mu, L->m_var, L->v_var};
+  const size_t b[kBufsPerLayer] = {W * 4, W * 4, W * 4, Wb * 2, Wb * 2, W * 4, Wb * 2,
+                                   (size_t)2 * kMaxPartials * sizeof(double), W * 4, W * 4, W * 4, W * 4};
+  for (int k = 0; k < kBufsPerLayer; ++k) { ptr[k] = p[k]; bytes[k] = p[k] ? b[k] : 0; }
+}
+
+inline bool layer_lrt(const vbnn_layer* L) {
+  return L->kind == VBNN_KIND_VB && L->opts.reparam == VBNN_REPARAM_LOCAL;
+}
+inline uint32_t* flag_ptr(const vbnn_peer* P, int q, size_t off, int j, int r) {
+  return reinterpret_cast<uint32_t*>(P->peer_block[q] + off) + (size_t)j * P->G + r;
+}
+
+// device-to-device copy of this rank's shard of one buffer to every other rank (copy engines)
+int push_shard(vbnn_peer* P, const PeerBuf& b, size_t off_bytes, size_t bytes) {
+  if (!b.ptr[P->me] || !bytes) return VBNN_OK;
+  for (int q = 0; q < P->G; ++q) {
+    if (q == P->me) continue;
+    VB_CUDA(cudaMemcpyAsync((char*)b.ptr[q] + off_bytes, (const char*)b.ptr[P->me] + off_bytes, bytes,
+                            cudaMemcpyDefault, P->side));
+  }
+  return VBNN_OK;
+}
+// the reverse: fetch every other owner's shard of a buffer that is not pushed during training
+int pull_shards(vbnn_peer* P, const PeerBuf& b, int O, size_t row_bytes, int rpo, cudaStream_t st) {
+  if (!b.ptr[P->me]) return VBNN_OK;
+  for (int q = 0; q < P->G; ++q) {
+    if (q == P->me) continue;
+    int r0, rows;
+    vbnn_peer_shard(O, P->G, q, &r0, &rows);
+    (void)rpo;
+    if (rows <= 0) continue;
+    VB_CUDA(cudaMemcpyAsync((char*)b.ptr[P->me] + (size_t)r0 * row_bytes, (const char*)b.ptr[q] + (size_t)r0 * row_bytes,
+                            (size_t)rows * row_bytes, cudaMemcpyDefault, st));
+  }
+  return VBNN_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ used by mlp.cu --------
+void peer_scatter(const vbnn_mlp* m, int j, EpiParams& p) {
+  const vbnn_peer* P = m->peer;
+  const PeerLayer& pl = P->layers[j];
+  const vbnn_layer* L = m->layers[j];
+  p.scatter_rows = pl.rpo;
+  for (int q = 0; q < 8; ++q) { p.gW_peer[q] = nullptr; p.gS_peer[q] = nullptr; }
+  for (int q = 0; q < P->G; ++q) {
+    float* slot = reinterpret_cast<float*>(P->peer_block[q] + pl.off_recv) + (size_t)P->me * pl.slot_floats;
+    // pre-biased: the epilogue indexes with the GLOBAL row
+    p.gW_peer[q] = slot - (long long)q * pl.rpo * L->I;
+    p.gS_peer[q] = L->kind == VBNN_KIND_VB ? p.gW_peer[q] + (size_t)pl.rpo * L->I : nullptr;
+  }
+}
+
+int peer_wait_params(vbnn_mlp* m) {
+  vbnn_peer* P = m->peer;
+  const int Lc = (int)m->layers.size();
+  k_wait_params<<<1, 256, 0, m->ctx->stream>>>(reinterpret_cast<const uint32_t*>(P->block + P->off_param_ready), P->seq,
+                                               Lc, P->G, P->d_err);
+  VB_CUDA(cudaGetLastError());
+  m->ctx->launches++;
+  return VBNN_OK;
+}
+
+int peer_after_dw(vbnn_mlp* m, int j) {
+  vbnn_peer* P = m->peer;
+  vbnn_ctx* c = m->ctx;
+  vbnn_layer* L = m->layers[j];
+  PeerLayer& pl = P->layers[j];
+  const int G = P->G, me = P->me;
+  // ---- main stream: gradBias to every rank, then "my gradients of layer j are out" ----
+  SignalGrad sg;
+  memset(&sg, 0, sizeof(sg));
+  sg.gb = L->gb; sg.O = L->O; sg.mseq = pl.mseq; sg.G = G;
+  for (int q = 0; q < G; ++q) {
+    sg.gb_dst[q] = reinterpret_cast<float*>(P->peer_block[q] + pl.off_gb) + (size_t)me * L->O;
+    sg.ready_dst[q] = flag_ptr(P, q, P->off_grad_ready, j, me);
+  }
+  k_signal_grad<<<1, 256, 0, c->stream>>>(sg);
+  VB_CUDA(cudaGetLastError());
+  VB_CUDA(cudaEventRecord(pl.ev_dw, c->stream));
+  // ---- side stream: wait for every rank, update this rank's rows, push, signal ----
+  cudaStream_t sd = P->side;
+  VB_CUDA(cudaStreamWaitEvent(sd, pl.ev_dw, 0));
+  k_wait_grad<<<1, 32, 0, sd>>>(flag_ptr(P, me, P->off_grad_ready, j, 0), pl.sseq, G, P->d_err);
+  VB_CUDA(cudaGetLastError());
+  const float* gb_slots = reinterpret_cast<const float*>(P->block + pl.off_gb);
+  float* slot0 = reinterpret_cast<float*>(P->block + pl.off_recv);
+  const size_t roff = (size_t)pl.row0 * L->I, roffb = (size_t)pl.row0 * L->ldI;
+  // bias (and the plain nn.Linear output layer): optim.sgd, VBLinear.lua:125-128 / mlp.lua:120-123;
+  // the bias is O floats: every rank applies the summed gradient itself
+  VB_TRY(launch_sgd_slots(L->bias, gb_slots, G, L->O, L->O, L->opts.lr_bias, nullptr, 1, 1, sd));
+  c->launches += 3;
+  if (L->kind == VBNN_KIND_LINEAR) {
+    if (pl.rows > 0) {
+      VB_TRY(launch_sgd_slots(L->weight + roff, slot0, G, (long long)pl.slot_floats, (long long)pl.rows * L->I,
+                              L->opts.lr_bias, L->w_bf16 ? L->w_bf16 + roffb : nullptr, L->I, L->ldI, sd));
+      c->launches++;
+      if (L->w_bf16) VB_TRY(push_shard(P, pl.w_bf16, roffb * 2, (size_t)pl.rows * L->ldI * 2));
+      else VB_TRY(push_shard(P, pl.weight, roff * 4, (size_t)pl.rows * L->I * 4));
+    }
+  } else {
+    UpdateParams u;
+    memset(&u, 0, sizeof(u));
+    u.mu = L->means + roff; u.lvar = L->lvars + roff;
+    u.gW = slot0; u.gS = slot0 + (size_t)pl.rpo * L->I;
+    u.n_src = G; u.src_stride = (long long)pl.slot_floats;
+    u.m_mu = L->m_mu + roff; u.v_mu = L->v_mu + roff; u.m_var = L->m_var + roff; u.v_var = L->v_var + roff;
+    u.mu_bf16 = L->mu_bf16 ? L->mu_bf16 + roffb : nullptr;
+    u.s2_bf16 = L->s2_bf16 ? L->s2_bf16 + roffb : nullptr;
+    u.ld_bf16 = L->ldI;
+    u.s2_f32 = L->s2_f32 ? L->s2_f32 + roff : nullptr;
+    u.O = pl.rows; u.I = L->I; u.W_total = (long long)L->O * L->I;
+    const int gq = L->n_part / G;
+    u.partials = L->prior_partials; u.n_partials = L->n_part;
+    u.next_partials = L->prior_partials; u.partials_pingpong = 1;
+    u.grid_override = gq; u.part_off = me * gq;
+    for (int q = 0; q < G; ++q)
+      if (q != me) u.peer_partials[u.n_peer++] = (double*)pl.partials.ptr[q];
+    u.var_hat_dev = L->var_hat_dev; u.t_dev = L->t_dev;
+    u.B = L->opts.B; u.S = (float)L->opts.S;
+    u.lr_mu = L->opts.lr_mu; u.lr_var = L->opts.lr_var;
+    u.beta1 = L->opts.adam_beta1; u.beta2 = L->opts.adam_beta2; u.eps = L->opts.adam_eps;
+    u.lrt = layer_lrt(L);
+    VB_TRY(launch_update(u, nullptr, sd));                                   // VBLinear.lua:130-143 on rows [row0, row0+rows)
+    c->launches++;
+    L->prior_valid = true;
+    if (pl.rows > 0) {
+      if (!layer_lrt(L)) {                       // weight sampling reads mu / log sigma^2 (VBLinear.lua:59)
+        VB_TRY(push_shard(P, pl.means, roff * 4, (size_t)pl.rows * L->I * 4));
+        VB_TRY(push_shard(P, pl.lvars, roff * 4, (size_t)pl.rows * L->I * 4));
+      } else if (L->mu_bf16) {                   // tensor-core operands of the LRT GEMMs
+        VB_TRY(push_shard(P, pl.mu_bf16, roffb * 2, (size_t)pl.rows * L->ldI * 2));
+        VB_TRY(push_shard(P, pl.s2_bf16, roffb * 2, (size_t)pl.rows * L->ldI * 2));
+      } else {                                   // fp32 LRT GEMM operands
+        VB_TRY(push_shard(P, pl.means, roff * 4, (size_t)pl.rows * L->I * 4));
+        VB_TRY(push_shard(P, pl.s2_f32, roff * 4, (size_t)pl.rows * L->I * 4));
+      }
+    }
+  }
+  SignalParam sp;
+  memset(&sp, 0, sizeof(sp));
+  for (int q = 0; q < G; ++q) sp.ready_dst[q] = flag_ptr(P, q, P->off_param_ready, j, me);
+  sp.sseq = pl.sseq; sp.t_dev = L->t_dev; sp.G = G;
+  k_signal_param<<<1, 32, 0, sd>>>(sp);
+  VB_CUDA(cudaGetLastError());
+  c->launches++;
+  P->stale = true;
+  return VBNN_OK;
+}
+
+int peer_check(vbnn_mlp* m) {
+  if (m->peer && m->peer->h_err && *m->peer->h_err) {
+    set_error("peer mode: a rank did not signal within %llu s (wait timed out); results are invalid",
+              kWaitTimeoutNs / 1000000000ull);
+    return VBNN_E_STATE;
+  }
+  return VBNN_OK;
+}
+
+void peer_destroy(vbnn_mlp* m) {
+  vbnn_peer* P = m->peer;
+  if (!P) return;
+  if (P->side) { cudaStreamSynchronize(P->side); cudaStreamDestroy(P->side); }
+  for (void* p : P->opened) cudaIpcCloseMemHandle(p);
+  for (PeerLayer& pl : P->layers) if (pl.ev_dw) cudaEventDestroy(pl.ev_dw);
+  if (P->ev_side) cudaEventDestroy(P->ev_side);
+  if (P->block) cudaFree(P->block);
+  if (P->h_err) cudaFreeHost(P->h_err);
+  for (vbnn_layer* L : m->layers) L->shard_stale = nullptr;
+  delete P;
+  m->peer = nullptr;
+}
+
+}  // namespace vbnn
+
+using namespace vbnn;
+
+// rows [row0, row0 + rows) of an O-row parameter matrix belong to `rank` of `nranks`; the shard
+// height is a multiple of 32 so that a 32-row epilogue chunk never straddles two owners
+extern "C" int vbnn_peer_shard(int O, int nranks, int rank, int* row0, int* rows) {
+  VB_CHECK(O > 0 && nranks >= 1 && rank >= 0 && rank < nranks, VBNN_E_INVALID, "vbnn_peer_shard: bad argument");
+  const int rpo = round_up(ceil_div(O, nranks), 32);
+  int r0 = rank * rpo;
+  if (r0 > O) r0 = O;
+  int r1 = r0 + rpo;
+  if (r1 > O) r1 = O;
+  if (row0) *row0 = r0;
+  if (rows) *rows = r1 - r0;
+  return rpo;
+}
+
+extern "C" int vbnn_mlp_peer_export(vbnn_mlp* m, void* blob, size_t capacity, size_t* blob_len) {
+  VB_CHECK(m && blob_len, VBNN_E_INVALID, "vbnn_mlp_peer_export: null argument");
+  vbnn_ctx* c = m->ctx;
+  const int G = c->nranks, Lc = (int)m->layers.size();
+  const size_t need = sizeof(BlobHeader) + (size_t)(1 + Lc * kBufsPerLayer) * sizeof(BlobEntry);
+  *blob_len = need;
+  if (!blob) return VBNN_OK;                                    // size query
+  VB_CHECK(capacity >= need, VBNN_E_INVALID, "vbnn_mlp_peer_export: blob needs %zu bytes", need);
+  VB_CHECK(G > 1 && G <= kMaxPeers, VBNN_E_UNSUPPORTED, "peer mode needs 2..%d ranks (vbnn_comm_init first)", kMaxPeers);
+  VB_CHECK(!m->opts.strict_reference, VBNN_E_UNSUPPORTED,
+           "peer mode does not shard the stdv / mu_sqe caches of strict_reference");
+  VB_CHECK(m->peer == nullptr, VBNN_E_STATE, "peer mode already set up");
+  VB_CUDA(cudaSetDevice(c->device));
+  vbnn_peer* P = new vbnn_peer();
+  m->peer = P;
+  P->G = G; P->me = c->rank;
+  P->layers.resize(Lc);
+  // ---- comm block layout (identical on every rank) ----
+  size_t off = 0;
+  P->off_grad_ready = off; off = align_up(off + (size_t)Lc * G * 4, 256);
+  P->off_param_ready = off; off = align_up(off + (size_t)Lc * G * 4, 256);
+  const size_t off_seq = off; off = align_up(off + (size_t)2 * Lc * 4, 256);
+  for (int j = 0; j < Lc; ++j) {
+    vbnn_layer* L = m->layers[j];
+    PeerLayer& pl = P->layers[j];
+    pl.rpo = vbnn_peer_shard(L->O, G, P->me, &pl.row0, &pl.rows);
+    pl.slot_floats = (size_t)pl.rpo * L->I * (L->kind == VBNN_KIND_VB ? 2 : 1);
+    pl.off_gb = off; off = align_up(off + (size_t)G * L->O * 4, 256);
+    pl.off_recv = off; off = align_up(off + (size_t)G * pl.slot_floats * 4, 256);
+  }
+  P->block_bytes = off;
+  cudaError_t e = cudaMalloc((void**)&P->block, off);
+  if (e != cudaSuccess) {
+    set_error("peer mode: cudaMalloc(%zu bytes) failed: %s", off, cudaGetErrorString(e));
+    peer_destroy(m);
+    return VBNN_E_NOMEM;
+  }
+  VB_CUDA(cudaMemsetAsync(P->block, 0, off, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  P->seq = reinterpret_cast<uint32_t*>(P->block + off_seq);
+  for (int j = 0; j < Lc; ++j) { P->layers[j].mseq = P->seq + 2 * j; P->layers[j].sseq = P->seq + 2 * j + 1; }
+  VB_CUDA(cudaHostAlloc((void**)&P->h_err, sizeof(int), cudaHostAllocMapped));
+  *P->h_err = 0;
+  VB_CUDA(cudaHostGetDevicePointer((void**)&P->d_err, P->h_err, 0));
+  // ---- the blob: IPC handle + offset of every buffer another rank touches ----
+  BlobHeader* h = reinterpret_cast<BlobHeader*>(blob);
+  h->magic = kBlobMagic; h->rank = (uint32_t)P->me; h->nranks = (uint32_t)G; h->n_entries = (uint32_t)(1 + Lc * kBufsPerLayer);
+  BlobEntry* en = reinterpret_cast<BlobEntry*>(h + 1);
+  VB_TRY(make_entry(P->block, P->block_bytes, &en[0]));
+  for (int j = 0; j < Lc; ++j) {
+    const void* ptr[kBufsPerLayer]; size_t bytes[kBufsPerLayer];
+    local_bufs(m->layers[j], ptr, bytes);
+    for (int k = 0; k < kBufsPerLayer; ++k) VB_TRY(make_entry(ptr[k], bytes[k], &en[1 + j * kBufsPerLayer + k]));
+  }
+  P->exported = true;
+  return VBNN_OK;
+}
+
+extern "C" int vbnn_mlp_peer_import(vbnn_mlp* m, const void* blobs, size_t blob_len) {
+  VB_CHECK(m && blobs, VBNN_E_INVALID, "vbnn_mlp_peer_import: null argument");
+  vbnn_peer* P = m->peer;
+  VB_CHECK(P && P->exported && !P->active, VBNN_E_STATE, "vbnn_mlp_peer_import: call vbnn_mlp_peer_export first");
+  vbnn_ctx* c = m->ctx;
+  const int G = P->G, Lc = (int)m->layers.size();
+  VB_CUDA(cudaSetDevice(c->device));
+  struct Opened { cudaIpcMemHandle_t h; char* base; };
+  for (int q = 0; q < G; ++q) {
+    const BlobHeader* h = reinterpret_cast<const BlobHeader*>((const char*)blobs + (size_t)q * blob_len);
+    VB_CHECK(h->magic == kBlobMagic && (int)h->rank == q && (int)h->nranks == G &&
+                 (int)h->n_entries == 1 + Lc * kBufsPerLayer,
+             VBNN_E_INVALID, "vbnn_mlp_peer_import: blob %d is not rank %d's export of the same network", q, q);
+    const BlobEntry* en = reinterpret_cast<const BlobEntry*>(h + 1);
+    std::vector<Opened> cache;
+    auto map = [&](const BlobEntry& e, void** out) -> int {
+      *out = nullptr;
+      if (!e.bytes) return VBNN_OK;
+      for (const Opened& o : cache)
+        if (memcmp(&o.h, &e.handle, sizeof(e.handle)) == 0) { *out = o.base + e.offset; return VBNN_OK; }
+      void* base = nullptr;
+      cudaError_t err = cudaIpcOpenMemHandle(&base, e.handle, cudaIpcMemLazyEnablePeerAccess);
+      if (err != cudaSuccess) {
+        set_error("cudaIpcOpenMemHandle (rank %d's buffer) failed: %s", q, cudaGetErrorString(err));
+        return VBNN_E_CUDA;
+      }
+      cache.push_back({e.handle, (char*)base});
+      P->opened.push_back(base);
+      *out = (char*)base + e.offset;
+      return VBNN_OK;
+    };
+    if (q == P->me) {
+      P->peer_block[q] = P->block;
+      for (int j = 0; j < Lc; ++j) {
+        const void* ptr[kBufsPerLayer]; size_t bytes[kBufsPerLayer];
+        local_bufs(m->layers[j], ptr, bytes);
+        for (int k = 0; k < kBufsPerLayer; ++k) layer_bufs(P->layers[j], k)->ptr[q] = const_cast<void*>(ptr[k]);
+      }
+      continue;
+    }
+    void* p = nullptr;
+    VB_TRY(map(en[0], &p));
+    P->peer_block[q] = (char*)p;
+    for (int j = 0; j < Lc; ++j)
+      for (int k = 0; k < kBufsPerLayer; ++k) {
+        VB_TRY(map(en[1 + j * kBufsPerLayer + k], &p));
+        layer_bufs(P->layers[j], k)->ptr[q] = p;
+      }
+  }
+  // the sigma_hat^2 partial sums: G x (blocks per shard) entries per half from now on
+  for (int j = 0; j < Lc; ++j) {
+    vbnn_layer* L = m->layers[j];
+    L->shard_stale = &P->stale;
+    if (L->kind != VBNN_KIND_VB) continue;
+    int gq = update_grid(P->layers[j].rpo, L->I);
+    if (gq > kMaxPartials / G) gq = kMaxPartials / G;
+    if (gq < 1) gq = 1;
+    L->n_part = gq * G;
+    VB_TRY(layer_refresh_prior_partials(L));
+  }
+  int lo = 0, hi = 0;
+  VB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  VB_CUDA(cudaStreamCreateWithPriority(&P->side, cudaStreamNonBlocking, hi));
+  VB_CUDA(cudaEventCreateWithFlags(&P->ev_side, cudaEventDisableTiming));
+  for (PeerLayer& pl : P->layers) VB_CUDA(cudaEventCreateWithFlags(&pl.ev_dw, cudaEventDisableTiming));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  P->active = true;
+  return VBNN_OK;
+}
+
+// Collective (host barrier before and after, on every rank): bring the fp32 state of the rows the
+// other ranks own up to date -- whatever training does not push: Adam moments always, plus mu /
+// log sigma^2 (LRT) or the nn.Linear weights (bf16) -- so that get / checkpoint / clamp_to_map see
+// the whole layer (utils.lua:73-80, main.lua:181).
+extern "C" int vbnn_mlp_sync_replicas(vbnn_mlp* m) {
+  VB_CHECK(m, VBNN_E_INVALID, "null mlp");
+  vbnn_peer* P = m->peer;
+  if (!P || !P->active) return VBNN_OK;
+  vbnn_ctx* c = m->ctx;
+  VB_CUDA(cudaSetDevice(c->device));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  VB_CUDA(cudaStreamSynchronize(P->side));
+  VB_TRY(peer_check(m));
+  for (size_t j = 0; j < m->layers.size(); ++j) {
+    vbnn_layer* L = m->layers[j];
+    PeerLayer& pl = P->layers[j];
+    const size_t rb = (size_t)L->I * 4;
+    if (L->kind == VBNN_KIND_LINEAR) {
+      if (L->w_bf16) VB_TRY(pull_shards(P, pl.weight, L->O, rb, pl.rpo, c->stream));
+      continue;
+    }
+    if (layer_lrt(L)) {
+      if (L->mu_bf16) VB_TRY(pull_shards(P, pl.means, L->O, rb, pl.rpo, c->stream));
+      VB_TRY(pull_shards(P, pl.lvars, L->O, rb, pl.rpo, c->stream));
+    }
+    VB_TRY(pull_shards(P, pl.m_mu, L->O, rb, pl.rpo, c->stream));
+    VB_TRY(pull_shards(P, pl.v_mu, L->O, rb, pl.rpo, c->stream));
+    VB_TRY(pull_shards(P, pl.m_var, L->O, rb, pl.rpo, c->stream));
+    VB_TRY(pull_shards(P, pl.v_var, L->O, rb, pl.rpo, c->stream));
+  }
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  P->stale = false;
+  return VBNN_OK;
+}
+
+extern "C" int vbnn_mlp_peer_active(const vbnn_mlp* m) { return m && m->peer && m->peer->active ? 1 : 0; }

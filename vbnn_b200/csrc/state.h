@@ -24,6 +24,10 @@ struct vbnn_ctx {
   std::vector<ProfRec> prof_recs;
   std::vector<cudaEvent_t> prof_pool;
   double prof_ms[8] = {0}; double prof_flops[8] = {0}; long long prof_n[8] = {0};
+  // phase marks of one minibatch (same switch): time from the previous mark to mark `id`
+  struct Mark { cudaEvent_t e; int id; };
+  std::vector<Mark> marks;
+  double phase_ms[16] = {0}; long long phase_n[16] = {0};
   // data parallel
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
@@ -44,6 +48,7 @@ struct vbnn_layer {
   float *m_mu = nullptr, *v_mu = nullptr, *m_var = nullptr, *v_var = nullptr;
   float *eps = nullptr, *stdv = nullptr, *mu_sqe = nullptr, *s2_f32 = nullptr;
   float* var_hat_dev = nullptr;
+  int n_part = 0;                    // partial sums per half (update_grid(O, I); peer mode: G x blocks per shard)
   double* prior_partials = nullptr;  // 2 x kMaxPartials: per-block sums written by the last update (ping-pong:
                                      // an update reads one half while its blocks write the other)
   // half (t & 1) holds the sums of the CURRENT parameters, t = the layer's device step counter
@@ -58,10 +63,42 @@ struct vbnn_layer {
   bool eps_injected = false;
   bool map_mode = false;
   bool prior_valid = false;
+  const bool* shard_stale = nullptr;  // peer mode: fp32 state of the rows other ranks own is out of date
+};
+
+// ---- peer mode (peer.cu): the data-parallel gradient exchange over NVLink peer memory -------
+// Rows [q*rpo, (q+1)*rpo) of every layer's parameters belong to rank q.  The dW GEMM epilogue
+// stores each gradient tile straight into its owner's receive slot (reduce-scatter fused into the
+// GEMM), the owner sums the G slots inside the fused KL + Adam update of its shard, and the copy
+// engines push the refreshed operands back to every rank (all-gather) while backward continues.
+constexpr int kMaxPeers = 8;
+struct PeerBuf { void* ptr[kMaxPeers] = {nullptr}; };   // ptr[q]: the buffer as mapped from rank q (ptr[me]: local)
+struct PeerLayer {
+  int rpo = 0, row0 = 0, rows = 0;       // rows per owner (multiple of 32), this rank's shard
+  size_t slot_floats = 0;                // floats per source slot {gW [, gS]}: rpo * I (* 2)
+  size_t off_recv = 0;                   // byte offset of slot 0 inside the comm block
+  size_t off_gb = 0;                     // byte offset of the [G][O] gradBias slots
+  PeerBuf means, lvars, s2_f32, mu_bf16, s2_bf16, weight, w_bf16, partials, m_mu, v_mu, m_var, v_var;
+  uint32_t *mseq = nullptr, *sseq = nullptr;   // step counters owned by the main / side stream
+  cudaEvent_t ev_dw = nullptr;
+};
+struct vbnn_peer {
+  int G = 1, me = 0;
+  char* block = nullptr; size_t block_bytes = 0;     // local comm block: flags | gb slots | receive slots
+  char* peer_block[kMaxPeers] = {nullptr};
+  size_t off_grad_ready = 0, off_param_ready = 0;    // uint32 [L][G] each
+  std::vector<PeerLayer> layers;
+  uint32_t* seq = nullptr;                           // local counters [2 * L]
+  int* h_err = nullptr; int* d_err = nullptr;        // pinned + mapped: set when a peer wait times out
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_side = nullptr;
+  std::vector<void*> opened;                         // IPC mappings to close
+  bool exported = false, active = false, stale = false;
 };
 
 struct vbnn_mlp {
   vbnn_ctx* ctx = nullptr;
+  vbnn_peer* peer = nullptr;
   std::vector<int> sizes;
   std::vector<vbnn_layer*> layers;   // hidden VB layers..., then the output layer
   int vb_output = 0, max_batch = 0, Z = 1;
@@ -102,7 +139,14 @@ int layer_compute_prior_internal(vbnn_layer* L);
 int layer_refresh_prior_partials(vbnn_layer* L);
 PhiloxStream layer_stream(const vbnn_layer* L, uint32_t kind, int sample);
 int comm_allreduce_internal(vbnn_ctx* ctx, float* buf, size_t count, cudaStream_t st);
+// peer mode (peer.cu)
+void peer_destroy(vbnn_mlp* m);
+void peer_scatter(const vbnn_mlp* m, int j, EpiParams& p);                // dW epilogue -> owners' slots
+int peer_wait_params(vbnn_mlp* m);                                        // main stream, before forward
+int peer_after_dw(vbnn_mlp* m, int j);                                    // signal + owner update + push
+int peer_check(vbnn_mlp* m);                                              // host: a peer wait timed out?
 // tensor-core GEMM launch with optional event bracketing (ctx->profiling)
 int tc_gemm(vbnn_ctx* ctx, int mode, const TcGemmArgs& g, const EpiParams& p);
 int prof_collect(vbnn_ctx* ctx);
+int prof_mark(vbnn_ctx* ctx, int id);     // id 0 starts a minibatch; no-op unless profiling
 }  // namespace vbnn

@@ -199,6 +199,29 @@ class MLP:
                 m.compute_prior()
         self.ctx.set_step(int(sd["step"]))
 
+    # ---- data parallel over NVLink peer memory (new; include/vbnn.h "peer mode") ----
+    def enable_peer(self, all_gather_bytes):
+        """all_gather_bytes(blob: bytes) -> list[bytes] in rank order (e.g. over torch.distributed).
+        After this, train_step / submit_host exchange gradients through the fused dW-epilogue
+        reduce-scatter + sharded update + copy-engine all-gather instead of an NCCL allreduce."""
+        n = C.c_size_t()
+        L.check(L.lib().vbnn_mlp_peer_export(self.handle, None, 0, C.byref(n)))
+        buf = (C.c_char * n.value)()
+        L.check(L.lib().vbnn_mlp_peer_export(self.handle, buf, n.value, C.byref(n)))
+        blobs = all_gather_bytes(bytes(buf))
+        if len(blobs) != self.ctx.nranks or any(len(b) != n.value for b in blobs):
+            raise L.VbnnError(L.E_INVALID, "enable_peer: all_gather_bytes must return one blob per rank")
+        joined = b"".join(blobs)
+        L.check(L.lib().vbnn_mlp_peer_import(self.handle, joined, n.value))
+
+    @property
+    def peer_active(self):
+        return bool(L.lib().vbnn_mlp_peer_active(self.handle))
+
+    def sync_replicas(self):
+        """Collective: call on every rank between two host barriers (see vbnn_mlp_sync_replicas)."""
+        L.check(L.lib().vbnn_mlp_sync_replicas(self.handle))
+
     def launch_count(self):
         v = C.c_longlong()
         L.check(L.lib().vbnn_mlp_launch_count(self.handle, C.byref(v)))
