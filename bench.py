@@ -311,6 +311,12 @@ def main():
     peaks = load_peaks()
     fps = flops_per_sample(w)
     roof = None
+    upd = prof.pop("update", None)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01c_c3_traffic.json")
+    if args.workload == "c3" and os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = dict(gemm_bytes_per_launch=tj["gemm_traffic_bytes_per_launch"], source=tj["source"])
     if prof:
         tot_ms = sum(v[0] for v in prof.values())
         tot_fl = sum(v[2] for v in prof.values())
@@ -318,7 +324,9 @@ def main():
         achieved = tot_fl / (tot_ms / 1e3) / 1e12
         roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 bf16, all epilogue classes)",
                     achieved=achieved, peak=peaks["tflops"], unit="TFLOP/s", frac=achieved / peaks["tflops"],
-                    peak_source=peaks["source"], peak_burst=peaks["tflops_burst"], traffic=None,
+                    peak_source=peaks["source"], peak_burst=peaks["tflops_burst"],
+                    traffic=traffic["gemm_bytes_per_launch"] if traffic else None,
+                    traffic_source=traffic["source"] if traffic else None,
                     launches=tot_n, avg_launch_ms=tot_ms / max(tot_n, 1), share_of_step=tot_ms / ms,
                     per_class={k: dict(tflops=v[2] / (v[0] / 1e3) / 1e12, ms_per_step=v[0] / args.steps, launches=v[1])
                                for k, v in prof.items()})
@@ -338,6 +346,12 @@ def main():
         line["e2e"] = e2e
     if roof:
         line["roofline"] = roof
+    if upd:
+        gbs = upd[2] / (upd[0] / 1e3) / 1e9
+        line["roofline_hbm"] = dict(bound="hbm", kernel="k_update (fused KL + 2x Adam, 56 B/weight algorithmic)", achieved=gbs,
+                                    peak=peaks["hbm"], unit="GB/s", frac=gbs / peaks["hbm"], launches=upd[1],
+                                    avg_launch_ms=upd[0] / max(upd[1], 1), share_of_step=upd[0] / ms,
+                                    peak_source=peaks["source"])
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(w, min(os.cpu_count() or 8, 64))
     elif not args.no_cpu_baseline:

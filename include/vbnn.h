@@ -115,7 +115,8 @@ int vbnn_ctx_destroy(vbnn_ctx* ctx);
 int vbnn_ctx_synchronize(vbnn_ctx* ctx);
 /* Per-launch device timing of the tensor-core GEMM: CUDA events on the context's stream around
  * every launch, summed per epilogue class (0 store, 1 fwd, 2 fwd-lrt, 3 dx, 4 dx-lrt, 5 dw,
- * 6 dw-lrt) together with the algorithmic flops.  Enabling it disables graph replay.  This is
+ * 6 dw-lrt) together with the algorithmic flops; class 7 is the fused KL + Adam update, whose
+ * "flops" slot holds its algorithmic HBM bytes (56 B per weight).  Enabling it disables graph replay.  This is
  * what bench.py's roofline object is computed from. */
 int vbnn_ctx_profile(vbnn_ctx* ctx, int enable);
 int vbnn_ctx_profile_read(vbnn_ctx* ctx, int cls, double* total_ms, long long* launches, double* flops);

@@ -41,7 +41,7 @@ class Context:
 
     def profile_read(self):
         """{class: (total_ms, launches, flops)} of the tensor-core GEMM launches since profile(True)."""
-        names = ["store", "fwd", "fwd_lrt", "dx", "dx_lrt", "dw", "dw_lrt"]
+        names = ["store", "fwd", "fwd_lrt", "dx", "dx_lrt", "dw", "dw_lrt", "update"]   # update: "flops" = bytes
         out = {}
         for cls, name in enumerate(names):
             ms, n, fl = C.c_double(), C.c_longlong(), C.c_double()

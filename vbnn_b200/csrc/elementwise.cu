@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(kThreads) k_prior_finalize(const double* parti
 //   -> one pass: 32 B read + 24 B written per weight (+ caches / operand copies).
 struct AdamCoef { float step_mu, step_var; };
 
-template <bool VEC, bool STATS>
-__global__ void __launch_bounds__(kThreads) k_update(UpdateParams p) {
+template <bool VEC, bool STATS, int TPB>
+__global__ void __launch_bounds__(TPB, TPB == 128 ? 6 : 1) k_update(UpdateParams p) {
   __shared__ double sh[32];
   __shared__ float s_var_hat;
   __shared__ AdamCoef s_coef;
@@ -271,6 +271,7 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateParams p) {
       const size_t idx = (p.partials_pingpong ? (size_t)((t_now + 1) & 1) * kMaxPartials : 0) + p.part_off + blockIdx.x;
       p.next_partials[idx] = r;
       for (int q = 0; q < p.n_peer; ++q) p.peer_partials[q][idx] = r;
+      for (int z = blockIdx.x + gridDim.x; z < p.zero_fill_to; z += gridDim.x) p.next_partials[idx - blockIdx.x + z] = 0.0;
     }
   }
   if (STATS) {
@@ -641,10 +642,11 @@ int launch_update(const UpdateParams& p, int* grid_out, cudaStream_t st) {
   const int grid = p.grid_override > 0 ? p.grid_override : update_grid(p.O, p.I);
   const bool vec = (p.I & 3) == 0;
   const bool stats = p.stat_partials != nullptr;
-  if (vec && stats) k_update<true, true><<<grid, kThreads, 0, st>>>(p);
-  else if (vec) k_update<true, false><<<grid, kThreads, 0, st>>>(p);
-  else if (stats) k_update<false, true><<<grid, kThreads, 0, st>>>(p);
-  else k_update<false, false><<<grid, kThreads, 0, st>>>(p);
+  if (p.coresident && vec && !stats) k_update<true, false, 128><<<grid, 128, 0, st>>>(p);
+  else if (vec && stats) k_update<true, true, kThreads><<<grid, kThreads, 0, st>>>(p);
+  else if (vec) k_update<true, false, kThreads><<<grid, kThreads, 0, st>>>(p);
+  else if (stats) k_update<false, true, kThreads><<<grid, kThreads, 0, st>>>(p);
+  else k_update<false, false, kThreads><<<grid, kThreads, 0, st>>>(p);
   VB_CUDA(cudaGetLastError());
   if (grid_out) *grid_out = grid;
   return VBNN_OK;

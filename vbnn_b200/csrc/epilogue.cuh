@@ -175,7 +175,7 @@ __device__ __forceinline__ void epi_quad(const EpiParams& p, const PhiloxStream&
     for (int j = 0; j < 4; ++j) {
       // sqrt(V) and zeta / (2 sqrt(V)) from one MUFU.RSQ (V = 0 only for an all-zero input row)
       const float v = a2[j];
-      const float rs = v > 0.f ? rsqrtf(v) : 0.f;
+      const float rs = v > 0.f ? rsqrt_fast(v) : 0.f;
       const float sq = v * rs;
       y[j] = a1[j] + b[j] + sq * zt[j];
       r[j] = 0.5f * zt[j] * rs;

@@ -114,8 +114,10 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug traps (the launch fails) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
+  long long t0 = 0;
+  for (uint32_t spins = 1; !mbar_try(bar, parity); ++spins) {
+    if ((spins & 1023u) != 0) continue;       // look at the clock once per 1024 polls: the poll loop shares
+    if (t0 == 0) { t0 = clock64(); continue; }   // issue slots with the epilogue warps
     if (clock64() - t0 > 4000000000LL) {
       printf("vbnn gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
@@ -290,7 +292,10 @@ struct TcCfg {
   static constexpr int ACC_COLS = NACC * BN;                        // TMEM columns per accumulator stage
   static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;    // double-buffered when it fits
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 2048;
+  // barriers + CLC ring live in the last 512 bytes; the dynamic window is declared 1024-byte aligned, so
+  // no alignment slack: together with the 1 KB the system reserves per CTA this leaves room on the SM
+  // for one small co-resident CTA of an HBM-bound kernel (the fused update overlaps the backward GEMMs)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 512;
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   static_assert(STAGES >= 2, "need at least a double-buffered smem ring");
   static_assert(B_ROWS % 64 == 0, "B tile rows per CTA must be a multiple of 64");
@@ -318,8 +323,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
   constexpr bool ZACC = epi_z_accumulates(MODE);
   constexpr int AS = C::ACC_STAGES;
 
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) {        // SWIZZLE_128B tiles need 1024-byte alignment
+    if (threadIdx.x == 0) printf("vbnn gemm_tc: dynamic shared memory base %u is not 1024-byte aligned\n", smem_base);
+    __trap();
+  }
   const uint32_t epi_stage_base = smem_base + C::STAGES * C::STAGE_BYTES;
   const uint32_t bar_base = epi_stage_base + EPI_STAGE_BYTES;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM address

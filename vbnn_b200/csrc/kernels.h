@@ -62,6 +62,10 @@ struct UpdateParams {
   int grid_override;                    // > 0: blocks of this launch
   int part_off;                         // this launch's first index in the next_partials array
   int n_peer; double* peer_partials[7]; // next_partials mirrored into the other ranks' arrays (peer stores)
+  // ---- co-resident variant: 128-thread blocks with <= 80 registers, one per SM, that fit beside a
+  // resident tcgen05 GEMM CTA, so the HBM-bound update overlaps the tensor-bound backward GEMMs ----
+  int coresident;
+  int zero_fill_to;                     // > grid: entries [grid, zero_fill_to) of next_partials are zeroed
 };
 int launch_update(const UpdateParams& p, int* grid_out, cudaStream_t st);
 

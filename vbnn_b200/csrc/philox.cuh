@@ -29,15 +29,11 @@ constexpr uint32_t kStreamZeta = 1u << 16;
 constexpr uint32_t kStreamInit = 2u << 16;
 
 __host__ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#ifdef __CUDA_ARCH__
-  uint32_t hi0 = __umulhi(0xD2511F53u, c[0]);
-  uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]);
-#else
-  uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * c[0]) >> 32);
-  uint32_t hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * c[2]) >> 32);
-#endif
-  uint32_t lo0 = 0xD2511F53u * c[0];
-  uint32_t lo1 = 0xCD9E8D57u * c[2];
+  // one 32 x 32 -> 64 multiply per product (IMAD.WIDE.U32 yields both halves)
+  const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+  const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+  const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+  const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
   uint32_t n0 = hi1 ^ c[1] ^ k0;
   uint32_t n2 = hi0 ^ c[3] ^ k1;
   c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
@@ -54,8 +50,17 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_
   }
 }
 
+// MUFU.RSQ without the denormal / IEEE fix-up sequence of rsqrtf()
+__device__ __forceinline__ float rsqrt_fast(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ float u32_to_unit(uint32_t x) {
-  return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0,1), 24 bits
+  // (n + 0.5) * 2^-24 in (0,1), 24 bits; as one FMA (a single rounding of the same real number, so
+  // bit-identical to ((float)n + 0.5f) * 2^-24)
+  return fmaf((float)(x >> 8), 1.0f / 16777216.0f, 1.0f / 33554432.0f);
 }
 
 // 4 standard normals for quad index `idx4` of the stream.
@@ -66,7 +71,7 @@ __device__ __forceinline__ void philox_normal4(const PhiloxStream& ps, uint32_t 
   for (int a = 0; a < 4; a += 2) {
     float u0 = u32_to_unit(c[a]), u1 = u32_to_unit(c[a + 1]);
     float t = -2.0f * __logf(u0);          // >= 0; exactly 0 when u0 rounds to 1.0 (p ~ 2^-25)
-    float r = t * rsqrtf(fmaxf(t, 1e-30f)); // sqrt via MUFU.RSQ (no IEEE slow path), 0 -> 0
+    float r = t * rsqrt_fast(fmaxf(t, 1e-30f)); // sqrt via MUFU.RSQ (no IEEE slow path), 0 -> 0
     float s, co;
     __sincosf(6.283185307179586f * u1, &s, &co);
     n[a] = r * co;
