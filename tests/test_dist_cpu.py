@@ -91,3 +91,87 @@ def test_philox_rows_are_shard_invariant():
     full = O.philox_normal_matrix(5, 3, 1 << 16, 0, rows=16, cols=12)
     parts = [O.philox_normal_matrix(5, 3, 1 << 16, 0, rows=8, cols=12, row0=r * 8) for r in range(2)]
     assert np.array_equal(np.concatenate(parts), full)
+
+
+# ---- peer mode (csrc/peer.cu): reduce-scatter by row owner, owner-only update, all-gather ----
+def _shard(O, G, q):
+    """vbnn_peer_shard through the C ABI (pure host code: loads without a GPU)."""
+    import ctypes as C
+    from vbnn_b200 import _lib as L
+    r0, rows = C.c_int(), C.c_int()
+    rpo = L.lib().vbnn_peer_shard(O, G, q, C.byref(r0), C.byref(rows))
+    return rpo, r0.value, rows.value
+
+
+def test_peer_shard_layout():
+    for O, G in [(4096, 8), (1000, 8), (10, 8), (1200, 2), (100, 4), (33, 2), (1, 8)]:
+        covered = []
+        rpos = set()
+        for q in range(G):
+            rpo, r0, rows = _shard(O, G, q)
+            rpos.add(rpo)
+            assert rpo % 32 == 0 and rpo * G >= O and 0 <= rows <= rpo
+            covered += list(range(r0, r0 + rows))
+        assert covered == list(range(O)), (O, G)      # a partition, in rank order
+        assert len(rpos) == 1
+
+
+def _peer_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import copy
+    O, opt, net = _make({"hidden": [40, 36]})
+    rng = np.random.RandomState(0)
+    N = 8
+    X = torch.from_numpy(rng.randn(N, 10))
+    T = torch.from_numpy(rng.randint(1, 4, N).astype(np.float64))
+    eps = [[torch.from_numpy(rng.randn(l.O, l.I)) for l in net.vb] for _ in range(opt["S"])]
+    ref = copy.deepcopy(net)
+    lo, hi = rank * N // world, (rank + 1) * N // world
+    _grads(O, net, opt, X[lo:hi], T[lo:hi], eps, scale_rows=(hi - lo) / N)
+    # "receive slots": every rank's accumulators, summed by the row owner in rank order
+    for lyr in net.vb:
+        slots = {}
+        for name in ("gradWeight", "gradSum", "gradBias"):
+            mine = getattr(lyr, name).clone()
+            allr = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            slots[name] = allr
+        rpo, r0, rows = _shard(lyr.O, world, rank)
+        lyr.gradBias.copy_(sum(slots["gradBias"]))                 # bias: every rank sums all slots
+        lyr.gradWeight.zero_(); lyr.gradSum.zero_()                # rows of other owners: never touched
+        lyr.gradWeight[r0:r0 + rows] = sum(s[r0:r0 + rows] for s in slots["gradWeight"])
+        lyr.gradSum[r0:r0 + rows] = sum(s[r0:r0 + rows] for s in slots["gradSum"])
+        before = (lyr.means.clone(), lyr.lvars.clone())
+        lyr.update(opt)                                            # sigma_hat^2 from the replicated parameters
+        # keep only the owned rows, then all-gather the shards
+        for t, old in zip((lyr.means, lyr.lvars), before):
+            own = t[r0:r0 + rows].clone()
+            t.copy_(old)
+            t[r0:r0 + rows] = own
+            for q in range(world):
+                _, q0, qrows = _shard(lyr.O, world, q)
+                buf = t[q0:q0 + qrows].clone()
+                dist.broadcast(buf, q)
+                t[q0:q0 + qrows] = buf
+    # single-process reference: full batch, ordinary update
+    _grads(O, ref, opt, X, T, eps, scale_rows=1.0)
+    for lyr in ref.vb:
+        lyr.update(opt)
+    err = 0.0
+    for a, b in zip(net.vb, ref.vb):
+        err = max(err, float((a.means - b.means).abs().max()), float((a.lvars - b.lvars).abs().max()),
+                  float((a.bias - b.bias).abs().max()))
+    ret[rank] = err
+    dist.destroy_process_group()
+
+
+def test_peer_reduce_scatter_sharded_update_allgather_equals_single():
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_peer_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert ret[r] < 1e-12, ret[r]
