@@ -238,7 +238,19 @@ def main():
                 out = [torch.empty_like(t) for _ in range(world)]
                 dist.all_gather(out, t)
                 return [bytes(o.cpu().tolist()) for o in out]
-            net.enable_peer(gather_bytes)
+            # every rank must agree: if CUDA IPC is unavailable anywhere, all fall back to the NCCL exchange
+            ok = 1
+            try:
+                net.enable_peer(gather_bytes)
+            except Exception as e:                                   # noqa: BLE001
+                ok = 0
+                print(f"[bench rank {rank}] peer mode unavailable ({e}); falling back to NCCL allreduce", file=sys.stderr)
+            flag = torch.tensor([ok], device=f"cuda:{local_rank}")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag[0]) == 0:
+                if net.peer_active:
+                    raise SystemExit("peer mode is active on this rank but not on all ranks")
+                dp_mode = "nccl (peer mode unavailable)"
     g = torch.Generator(device="cpu").manual_seed(3 + rank)
     nbuf = 2
     Xd = [torch.randn(N, w["sizes"][0], generator=g).cuda() for _ in range(nbuf)]

@@ -317,3 +317,88 @@ def test_epoch_loops_device_resident(ctx):
         assert math.isfinite(err) and 0.0 <= acc <= 100.0 and math.isfinite(terr) and 0.0 <= tacc <= 100.0
         res.append((acc, err, tacc, terr))
     assert np.allclose(res[0], res[1], rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("sizes,N,S,reparam", [([13, 7, 2], 1, 1, "weight"),        # one row, odd widths, 2 classes
+                                              ([13, 7, 2], 3, 3, "local"),
+                                              ([784, 100, 10], 100, 1, "weight"),  # BASELINE C1 exactly
+                                              ([33, 129, 65, 3], 130, 2, "weight"),  # every dim ragged vs 32/64/128 tiles
+                                              ([33, 129, 65, 3], 257, 2, "local")])
+def test_ragged_and_tiny_shapes_vs_oracle(ctx, precision, sizes, N, S, reparam):
+    """Edge shapes (rows / features that are not multiples of the 8-element TMA pitch, the 32-row
+    epilogue chunk or the 128 / 256 tile; a single-row minibatch; two classes) through vbnn_mlp_step."""
+    bf = precision == "bf16"
+    net, ref, gopt, oopt = build_pair(ctx, sizes, N, S, 30.0, precision, reparam, seed=3,
+                                      operand_round=O.round_bf16 if bf else None)
+    rng = np.random.RandomState(8)
+    nvb = len(ref.vb_all)
+    for it in range(2):
+        Xn = rng.randn(N, sizes[0]); Tn = rng.randint(1, sizes[-1] + 1, N).astype(np.float64)
+        step = ctx.get_step()
+        noise = [[torch.from_numpy(cpu(net.model[k].draw_noise(step, s, rows=N)).astype(np.float64))
+                  for k in range(nvb)] for s in range(S)]
+        err, acc = net.train_step(torch.from_numpy(Xn).float().cuda(), torch.from_numpy(Tn).float().cuda())
+        kw = dict(zeta=noise) if reparam == "local" else dict(eps=noise)
+        rerr, racc, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), **kw)
+        assert abs(err - rerr) < (5e-3 if bf else 1e-4) * abs(rerr), (it, err, rerr)
+        for k, ol in enumerate(ref.vb_all):
+            gl = net.model[k]
+            assert rel(cpu(gl.gradWeight), accs[k][0].numpy()) < (1e-2 if bf else 1e-5), (it, k)
+            assert rel(cpu(gl.gradSum), accs[k][1].numpy()) < (2e-2 if bf else 2e-5), (it, k)
+            assert rel(cpu(gl.means), ol.means.numpy()) < (5e-3 if bf else 2e-4), (it, k)
+            assert rel(cpu(gl.lvars), ol.lvars.numpy()) < (5e-3 if bf else 2e-4), (it, k)
+        assert rel(cpu(net.model[-1].weight), ref.out.weight.numpy()) < (5e-3 if bf else 2e-4)
+
+
+def test_batch_larger_than_max_batch_is_rejected(ctx):
+    from vbnn_b200 import _lib as L
+    net, _, _, _ = build_pair(ctx, [13, 7, 2], 4, 1, 30.0, "fp32", "weight")
+    X = torch.zeros(5, 13).cuda(); T = torch.ones(5).cuda()
+    with pytest.raises(L.VbnnError) as e:
+        net.train_step(X, T)
+    assert e.value.code == L.E_INVALID
+
+
+def test_convnet_head_behind_the_same_abi(ctx):
+    """BASELINE configs[3] (convnet.lua:14-33): the conv feature extractor is stock library code
+    (torch / cuDNN here, cunn in the reference); its 2-layer VBLinear head -- VBLinear(256,100) + ReLU
+    + VBLinear(100,C), both sampled (vb_indices = {8,10}, convnet.lua:9) -- runs through the layer-level
+    C ABI on the extractor's output, and the gradient w.r.t. the features flows back into it."""
+    import vbnn_b200
+    from vbnn_b200 import _lib as L
+    torch.manual_seed(0)
+    N, C = 64, 10
+    conv = torch.nn.Sequential(torch.nn.Conv2d(3, 16, 5), torch.nn.ReLU(), torch.nn.MaxPool2d(2),      # convnet.lua:14-20
+                               torch.nn.Conv2d(16, 16, 5), torch.nn.ReLU(), torch.nn.MaxPool2d(2),
+                               torch.nn.Flatten(), torch.nn.Linear(16 * 5 * 5, 256), torch.nn.ReLU()).cuda()
+    opt = vbnn_b200.default_opt(S=1, B=50.0, batchSize=N, mu_init=1, var_init=0.01, strict_reference=False, log=False)
+    h1 = vbnn_b200.VBLinear(256, 100, opt, ctx)
+    h2 = vbnn_b200.VBLinear(100, C, opt, ctx)
+    x = torch.randn(N, 3, 32, 32, device="cuda")
+    t = torch.randint(0, C, (N,), device="cuda")
+    feats = conv(x)
+    f = feats.detach().contiguous()
+    for h in (h1, h2):
+        h.resetAcc(); h.sample(sample_idx=0)
+    a1 = h1.updateOutput(f)
+    r1 = torch.clamp(a1, min=0)
+    logits = h2.updateOutput(r1).clone().requires_grad_(True)
+    loss = torch.nn.functional.cross_entropy(logits, t)
+    loss.backward()
+    g2 = logits.grad.contiguous()
+    gr1 = h2.updateGradInput(r1, g2); h2.accGradParameters(r1, g2)
+    g1 = (gr1 * (a1 > 0)).contiguous()
+    gf = h1.updateGradInput(f, g1); h1.accGradParameters(f, g1)
+    feats.backward(gf)                                     # into the stock extractor
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in conv.parameters())
+    # the head's data gradient equals autograd through the same sampled weights
+    W1 = h1.get(L.BUF_WEIGHT).cuda(); W2 = h2.get(L.BUF_WEIGHT).cuda()
+    f2 = f.clone().requires_grad_(True)
+    l2 = torch.nn.functional.cross_entropy(torch.clamp(f2 @ W1.t() + h1.bias, min=0) @ W2.t() + h2.bias, t)
+    l2.backward()
+    assert rel(cpu(gf), cpu(f2.grad)) < 1e-4
+    assert abs(l2.item() - loss.item()) < 1e-4 * abs(loss.item())
+    before = cpu(h1.means).copy()
+    h1.update(opt); h2.update(opt)                         # convnet.lua:105-117
+    assert not np.array_equal(cpu(h1.means), before)
