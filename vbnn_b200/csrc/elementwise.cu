@@ -264,6 +264,21 @@ __global__ void __launch_bounds__(TPB, TPB == 128 ? 6 : 1) k_update(UpdateParams
         for (int j = 0; j < nv; ++j) { d1[j] = __float2bfloat16_rn(mu[j]); d2[j] = __float2bfloat16_rn(s2_new[j]); }
       }
     }
+    for (int q = 0; q < p.n_push; ++q) {                 // peer mode, layer 0: all-gather by NVLink stores
+      if (p.push_mu[q]) store(p.push_mu[q], mu);
+      if (p.push_lv[q]) store(p.push_lv[q], lv);
+      if (p.push_s2[q]) store(p.push_s2[q], s2_new);
+      if (p.push_mu16[q]) {
+        bf16* d1 = p.push_mu16[q] + (long long)o * p.ld_bf16 + i0;
+        bf16* d2 = p.push_s216[q] + (long long)o * p.ld_bf16 + i0;
+        if (nv == 4) {
+          st4_bf16(d1, mu[0], mu[1], mu[2], mu[3]);
+          st4_bf16(d2, s2_new[0], s2_new[1], s2_new[2], s2_new[3]);
+        } else {
+          for (int j = 0; j < nv; ++j) { d1[j] = __float2bfloat16_rn(mu[j]); d2[j] = __float2bfloat16_rn(s2_new[j]); }
+        }
+      }
+    }
   }
   if (p.next_partials) {
     double r = block_sum((double)nxt, sh);

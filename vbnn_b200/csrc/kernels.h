@@ -62,6 +62,11 @@ struct UpdateParams {
   int grid_override;                    // > 0: blocks of this launch
   int part_off;                         // this launch's first index in the next_partials array
   int n_peer; double* peer_partials[7]; // next_partials mirrored into the other ranks' arrays (peer stores)
+  // all-gather fused into the update (used for layer 0, whose update is the tail of a minibatch and has
+  // idle SMs and idle NVLink to itself): every refreshed operand quad is also stored to the n_push
+  // other ranks; pointers pre-offset like their local counterparts, nullptr = not pushed
+  int n_push;
+  bf16* push_mu16[7]; bf16* push_s216[7]; float* push_mu[7]; float* push_lv[7]; float* push_s2[7];
   // ---- co-resident variant: 128-thread blocks with <= 80 registers, one per SM, that fit beside a
   // resident tcgen05 GEMM CTA, so the HBM-bound update overlaps the tensor-bound backward GEMMs ----
   int coresident;

@@ -212,9 +212,13 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
     if (L->eps_injected && Zrun == 1 && L->eps) p.noise = L->eps;      // parity mode: injected epsilon
     if (scatter) peer_scatter(m, j, p);                                // reduce-scatter fused into the epilogue
     const int mode = lrt ? EPI_DW_LRT : EPI_DW;
-    static int split_env = -1;
-    if (split_env < 0) { const char* e = getenv("VBNN_DW_SPLIT"); split_env = e ? atoi(e) : 0; }
-    if (m->bf16 && lrt && split_env) {
+    // Dual dW (one launch, two accumulators, single-buffered TMEM) or two single-accumulator GEMMs
+    // (double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1).  On one GPU they tie; in
+    // peer mode the epilogue's stores cross NVLink and the split form hides them (8 GPUs: 6.14 -> 5.97 ms).
+    static int split_env = -2;
+    if (split_env == -2) { const char* e = getenv("VBNN_DW_SPLIT"); split_env = e ? atoi(e) : -1; }
+    const bool split = split_env >= 0 ? split_env != 0 : scatter;
+    if (m->bf16 && lrt && split) {
       // The two LRT parameter gradients are independent (g_mu = G^T X, g_s = H^T X^2): as two
       // single-accumulator GEMMs each tile needs half the TMEM, so the accumulator is double-buffered
       // and the epilogue of tile i hides behind the MMAs of tile i+1 (the dual kernel cannot).
@@ -230,6 +234,8 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
       g.A1 = {(const bf16*)m->H[j], ldo, 0, zs_out};
       g.B1 = {(const bf16*)m->act2[j], ldi, 0, zs_in};
       p1.gW = L->gS;                      // plain accumulate of H^T X^2 into gradSum
+      if (p1.scatter_rows)                // ... or into the owners' gradSum receive slots
+        for (int q = 0; q < 8; ++q) p1.gW_peer[q] = p.gS_peer[q];
       p1.scale = 1.f;
       VB_TRY(tc_gemm(m->ctx, EPI_DW, g, p1));
     } else if (m->bf16) {

@@ -260,6 +260,11 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     u.partials = L->prior_partials; u.n_partials = L->n_part;
     u.next_partials = L->prior_partials; u.partials_pingpong = 1;
     u.grid_override = gq; u.part_off = me * gq;
+    // Layers > 0 are updated while the persistent GEMM CTAs of the layers below own every SM: use the
+    // 128-thread / 80-register variant that fits beside them (a full-width kernel would only start at
+    // the next kernel boundary and push the whole chain into the tail of the minibatch).  Layer 0's
+    // update runs after the last GEMM: full width.
+    u.coresident = j > 0 ? 1 : 0;
     for (int q = 0; q < G; ++q)
       if (q != me) u.peer_partials[u.n_peer++] = (double*)pl.partials.ptr[q];
     u.var_hat_dev = L->var_hat_dev; u.t_dev = L->t_dev;
@@ -267,10 +272,28 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     u.lr_mu = L->opts.lr_mu; u.lr_var = L->opts.lr_var;
     u.beta1 = L->opts.adam_beta1; u.beta2 = L->opts.adam_beta2; u.eps = L->opts.adam_eps;
     u.lrt = layer_lrt(L);
+    static int l0_env = -1;
+    if (l0_env < 0) { const char* e = getenv("VBNN_PEER_L0_PUSH"); l0_env = (e && !strcmp(e, "ce")) ? 0 : 1; }
+    const bool fused_push = j == 0 && l0_env && pl.rows > 0;
+    if (fused_push) {
+      // layer 0: its update is the tail of the minibatch -- the SMs and NVLink are otherwise idle, so the
+      // kernel stores the refreshed operands to every rank itself instead of 2 x (G-1) serial copies
+      for (int q = 0; q < G; ++q) {
+        if (q == me) continue;
+        const int i = u.n_push++;
+        if (!layer_lrt(L)) {
+          u.push_mu[i] = (float*)pl.means.ptr[q] + roff; u.push_lv[i] = (float*)pl.lvars.ptr[q] + roff;
+        } else if (L->mu_bf16) {
+          u.push_mu16[i] = (bf16*)pl.mu_bf16.ptr[q] + roffb; u.push_s216[i] = (bf16*)pl.s2_bf16.ptr[q] + roffb;
+        } else {
+          u.push_mu[i] = (float*)pl.means.ptr[q] + roff; u.push_s2[i] = (float*)pl.s2_f32.ptr[q] + roff;
+        }
+      }
+    }
     VB_TRY(launch_update(u, nullptr, sd));                                   // VBLinear.lua:130-143 on rows [row0, row0+rows)
     c->launches++;
     L->prior_valid = true;
-    if (pl.rows > 0) {
+    if (pl.rows > 0 && !fused_push) {
       if (!layer_lrt(L)) {                       // weight sampling reads mu / log sigma^2 (VBLinear.lua:59)
         VB_TRY(push_shard(P, pl.means, roff * 4, (size_t)pl.rows * L->I * 4));
         VB_TRY(push_shard(P, pl.lvars, roff * 4, (size_t)pl.rows * L->I * 4));
@@ -449,6 +472,7 @@ extern "C" int vbnn_mlp_peer_import(vbnn_mlp* m, const void* blobs, size_t blob_
     if (L->kind != VBNN_KIND_VB) continue;
     int gq = update_grid(P->layers[j].rpo, L->I);
     if (gq > kMaxPartials / G) gq = kMaxPartials / G;
+    if (gq > kNumSMs) gq = kNumSMs;      // one co-resident CTA per SM (see peer_after_dw)
     if (gq < 1) gq = 1;
     L->n_part = gq * G;
     VB_TRY(layer_refresh_prior_partials(L));
