@@ -119,6 +119,35 @@ class ClockSampler:
                     samples=len(sm), power_w_max=max(pw) if pw else None)
 
 
+def bind_to_gpu_numa_node(index):
+    """Host side of the end-to-end path: run this rank's host thread (and so first-touch its pinned staging
+    buffers) on the NUMA node the GPU hangs off, so that 8 ranks x 134 MB per minibatch do not cross the
+    socket interconnect.  Best effort; returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, z = part.partition("-")
+            cpus.update(range(int(a), int(z or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:                                            # noqa: BLE001
+        pass
+    return None
+
+
 def build_net(w, ctx, N):
     import vbnn_b200
     s = w["sizes"]
@@ -217,6 +246,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local_rank}"))
+    numa = bind_to_gpu_numa_node(local_rank)
     ctx = vbnn_b200.Context(local_rank, seed=5)
     if world > 1:
         def bcast(buf):
@@ -346,7 +376,7 @@ def main():
                 warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16" if w["precision"] == "bf16" else "f32", data="synthetic",
                 config=dict(workload=w["desc"], sizes=w["sizes"], global_batch=N * world, per_gpu_batch=N, S=w["S"],
-                            reparam=w["reparam"], parallelism=f"dp{world}", dp_exchange=dp_mode, output_layer="nn.Linear (mlp.lua:29)",
+                            reparam=w["reparam"], parallelism=f"dp{world}", dp_exchange=dp_mode, host_numa_node=numa, output_layer="nn.Linear (mlp.lua:29)",
                             l2="working set (parameters + optimizer state + activations) >> 126 MB L2; two "
                                "alternating input minibatches",
                             flops_per_sample=fps),

@@ -720,8 +720,49 @@ int launch_finalize_result(const float* acc, int Z, int N, float* out2, cudaStre
   return VBNN_OK;
 }
 
+// bf16 rows with 16-byte pitch: one thread owns 8 consecutive columns (one 16-byte load per row), a
+// warp covers 512 contiguous bytes of a row, a block 8 rows per iteration
+__global__ void __launch_bounds__(256) k_colsum_bf16x8(const bf16* G, long long rows, int cols, int ld, float scale,
+                                                        float* gb) {
+  __shared__ float sh[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col0 = (blockIdx.x * 32 + tx) * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col0 < ld) {
+    for (long long r = (long long)blockIdx.y * 8 + ty; r < rows; r += (long long)gridDim.y * 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(G + r * ld + col0);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += __uint_as_float(w[k] << 16);
+        acc[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sh[ty][tx][k] = acc[k];
+  __syncthreads();
+  // 256 threads reduce the 8 row-groups of the block's 256 columns
+  const int c = threadIdx.x;
+  float s = 0.f;
+#pragma unroll
+  for (int g = 0; g < 8; ++g) s += sh[g][c >> 3][c & 7];
+  const int col = blockIdx.x * 256 + c;
+  if (col < cols) atomicAdd(gb + col, scale * s);
+}
+
 int launch_colsum(const void* G, int is_bf16, long long rows, int cols, int ld, float scale, float* gb,
                   cudaStream_t st) {
+  if (is_bf16 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0 && cols >= 256) {
+    long long ry = (rows + 63) / 64;
+    if (ry < 1) ry = 1;
+    const int gx = ceil_div(cols, 256);
+    const long long cap = (long long)kNumSMs * 4 / gx > 1 ? (long long)kNumSMs * 4 / gx : 1;
+    if (ry > cap) ry = cap;
+    k_colsum_bf16x8<<<dim3(gx, (int)ry), 256, 0, st>>>((const bf16*)G, rows, cols, ld, scale, gb);
+    VB_CUDA(cudaGetLastError());
+    return VBNN_OK;
+  }
   long long ry = (rows + 255) / 256;
   if (ry < 1) ry = 1;
   if (ry > 64) ry = 64;
