@@ -10,6 +10,8 @@
 //   EPI_DW       VBLinear:accGradParameters: gradWeight += s*G^T X and
 //                gradSum += (G^T X) .* eps from ONE GEMM                    (VBLinear.lua:113-115)
 //   EPI_DW_LRT   A12 parameter gradients (two accumulators)
+//   EPI_FWD_LRT2 / EPI_DX_LRT2  the same A12 forward / backward-data maths with one of the two products
+//                read back from global memory instead of a second TMEM accumulator
 #pragma once
 #include "common.cuh"
 #include "philox.cuh"
@@ -24,6 +26,11 @@ enum EpiMode : int {
   EPI_DX_LRT = 4,
   EPI_DW = 5,
   EPI_DW_LRT = 6,
+  // Second halves of the SPLIT local-reparameterisation GEMMs (tensor-core engine): the first half is a
+  // plain EPI_STORE GEMM that leaves its fp32 accumulator in `aux`; the second half's single accumulator
+  // (TMEM double-buffered, so this heavy epilogue overlaps the next tile's MMAs) is joined with `aux`.
+  EPI_FWD_LRT2 = 7,          // acc = X^2 s2^T (variance), aux = X mu^T (mean)
+  EPI_DX_LRT2 = 8,           // acc = G mu, aux = H s2
 };
 
 __host__ __device__ constexpr bool epi_is_dual(int mode) {
@@ -59,6 +66,8 @@ struct EpiParams {
   // pre-biased so that row * ld_g + col indexes them like gW / gS); 0 = plain local gW / gS
   int scatter_rows;
   float* gW_peer[8]; float* gS_peer[8];
+  // split LRT modes: the other product, fp32 [M x ld_aux] (+ z * zs_aux)
+  const float* aux; int ld_aux; long long zs_aux;
 };
 
 // destination of a dW tile whose rows all share one owner (32-row warp chunks: scatter_rows % 32 == 0)
@@ -139,7 +148,23 @@ __device__ __forceinline__ void load_bias4(const float* bias, int col, int nvali
 // Process one quad.  a1/a2: accumulator values (a2 only for dual modes).
 template <int MODE, typename AT>
 __device__ __forceinline__ void epi_quad(const EpiParams& p, const PhiloxStream& ps0, int z, int row, int col,
+                                         const float (&a1)[4], const float (&a2)[4]);
+
+// split modes: fetch the other product, then run the dual-mode code
+template <int MODE, typename AT>
+__device__ __forceinline__ void epi_quad_split(const EpiParams& p, const PhiloxStream& ps0, int z, int row, int col,
+                                               const float (&acc)[4]) {
+  if (row >= p.M || col >= p.N) return;
+  float o[4];
+  load4<float>(p.aux + z * p.zs_aux + (long long)row * p.ld_aux + col, o, min(4, p.N - col), (p.ld_aux & 3) == 0);
+  if constexpr (MODE == EPI_FWD_LRT2) epi_quad<EPI_FWD_LRT, AT>(p, ps0, z, row, col, o, acc);     // (mean, variance)
+  else epi_quad<EPI_DX_LRT, AT>(p, ps0, z, row, col, acc, o);                                    // (G mu, H s2)
+}
+
+template <int MODE, typename AT>
+__device__ __forceinline__ void epi_quad(const EpiParams& p, const PhiloxStream& ps0, int z, int row, int col,
                                          const float (&a1)[4], const float (&a2)[4]) {
+  if constexpr (MODE == EPI_FWD_LRT2 || MODE == EPI_DX_LRT2) { epi_quad_split<MODE, AT>(p, ps0, z, row, col, a1); return; }
   if (row >= p.M || col >= p.N) return;
   const int nvalid = min(4, p.N - col);
   const bool vec_act = (p.ld_act & 3) == 0;

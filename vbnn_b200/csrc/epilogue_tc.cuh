@@ -130,6 +130,7 @@ inline bool epi_can_stage(int mode, const EpiParams& p) {
   if (!ok_act(p.out_act, p.ld_act) || !ok_act(p.out_act2, p.ld_act) || !ok_act(p.r_out, p.ld_act) || (p.zs_act % 8) != 0) return false;
   if (!ok_act(p.xprev, p.ld_x) || !ok_act(p.rprev, p.ld_x) || (p.zs_x % 8) != 0) return false;
   if (!ok_f32(p.gW, p.ld_g) || !ok_f32(p.gS, p.ld_g)) return false;
+  if (!ok_f32(p.aux, p.ld_aux) || (p.zs_aux % 4) != 0) return false;
   if (p.scatter_rows)
     for (int q = 0; q < 8; ++q)
       if (!ok_f32(p.gW_peer[q], p.ld_g) || !ok_f32(p.gS_peer[q], p.ld_g)) return false;
@@ -145,6 +146,14 @@ __device__ __forceinline__ void epi_chunk_staged(const EpiParams& p, const Philo
                                                  int col0, const float (&v1)[32], const float (&v2)[32], uint32_t stage) {
   const int rows_valid = min(32, p.M - row0);        // <= 0 never happens: the caller skips such warps
   const int row = row0 + lane;
+  if constexpr (MODE == EPI_FWD_LRT2 || MODE == EPI_DX_LRT2) {
+    // split LRT: the other product comes from global memory (coalesced through the staging tile)
+    float o[32];
+    get_tile_f32(stage, lane, p.aux + z * p.zs_aux + (long long)row0 * p.ld_aux + col0, p.ld_aux, rows_valid, o);
+    if constexpr (MODE == EPI_FWD_LRT2) epi_chunk_staged<EPI_FWD_LRT>(p, ps0, z, row0, lane, col0, o, v1, stage);
+    else epi_chunk_staged<EPI_DX_LRT>(p, ps0, z, row0, lane, col0, v1, o, stage);
+    return;
+  }
   if constexpr (MODE == EPI_STORE) {
     put_tile_f32(stage, lane, p.out_f32 + z * p.zs_f32 + (long long)row0 * p.ld_f32 + col0, p.ld_f32, rows_valid, v1);
   } else if constexpr (MODE == EPI_FWD) {

@@ -791,6 +791,12 @@ int gemm_tc_launch(int mode, const TcGemmArgs& g, const EpiParams& p, cudaStream
     case EPI_DX_LRT:
       VB_CHECK(ak && !bk, VBNN_E_INVALID, "EPI_DX_LRT expects K-major A, MN-major B");
       return launch_any<EPI_DX_LRT, true, false>(g, p, st);
+    case EPI_FWD_LRT2:
+      VB_CHECK(ak && bk && p.aux, VBNN_E_INVALID, "EPI_FWD_LRT2 expects K-major operands and the mean product");
+      return launch_any<EPI_FWD_LRT2, true, true>(g, p, st);
+    case EPI_DX_LRT2:
+      VB_CHECK(ak && !bk && p.aux, VBNN_E_INVALID, "EPI_DX_LRT2 expects K-major A, MN-major B and the H s2 product");
+      return launch_any<EPI_DX_LRT2, true, false>(g, p, st);
     case EPI_DW:
       VB_CHECK(!ak && !bk, VBNN_E_INVALID, "EPI_DW expects MN-major operands");
       return launch_any<EPI_DW, false, false>(g, p, st);

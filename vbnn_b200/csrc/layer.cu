@@ -283,7 +283,7 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t, cudaStr
   return VBNN_OK;
 }
 
-int tc_gemm(vbnn_ctx* c, int mode, const TcGemmArgs& g, const EpiParams& p) {
+int tc_gemm(vbnn_ctx* c, int mode, const TcGemmArgs& g, const EpiParams& p, int prof_cls) {
   if (!c->profiling) return gemm_tc_launch(mode, g, p, c->stream, &c->launches);
   auto get_event = [&](cudaEvent_t* e) -> int {
     if (!c->prof_pool.empty()) { *e = c->prof_pool.back(); c->prof_pool.pop_back(); return VBNN_OK; }
@@ -293,7 +293,7 @@ int tc_gemm(vbnn_ctx* c, int mode, const TcGemmArgs& g, const EpiParams& p) {
   vbnn_ctx::ProfRec r;
   VB_TRY(get_event(&r.a));
   VB_TRY(get_event(&r.b));
-  r.cls = mode;
+  r.cls = prof_cls >= 0 ? prof_cls : mode;
   r.flops = 2.0 * g.M * (double)g.N * g.K * g.batch * (epi_is_dual(mode) ? 2.0 : 1.0);
   VB_CUDA(cudaEventRecord(r.a, c->stream));
   int rc = gemm_tc_launch(mode, g, p, c->stream, &c->launches);

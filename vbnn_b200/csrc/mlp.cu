@@ -27,6 +27,15 @@ inline bool layer_lrt(const vbnn_layer* L) {
   return L->kind == VBNN_KIND_VB && L->opts.reparam == VBNN_REPARAM_LOCAL;
 }
 inline int nlayers(const vbnn_mlp* m) { return (int)m->layers.size(); }
+// LRT forward / backward-data as two single-accumulator GEMMs (default) or one dual-accumulator GEMM
+// (VBNN_LRT_SPLIT bit 0: forward, bit 1: backward-data).  Measured on C3 under the 1000 W cap: the split
+// forward is 7 % faster (its Philox-heavy epilogue hides under the MMAs), the split backward-data 3 %
+// slower (its light epilogue gains nothing and the extra fp32 round trip costs energy) -> default 1.
+inline bool lrt_split(const vbnn_mlp* m, int which) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("VBNN_LRT_SPLIT"); env = e ? atoi(e) : 1; }
+  return (env & which) != 0 && m->aux != nullptr;
+}
 
 // ---- stage the caller's minibatch into operand form (outside the graph: pointers vary) ----
 int stage_input(vbnn_mlp* m, const float* X, const float* T, int N) {
@@ -110,6 +119,20 @@ int forward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, bool map_mod
     g.A1 = {(const bf16*)m->act[j], ldi, 1, zs_in};
     const bf16* w = layer_lrt(L) ? L->mu_bf16 : L->w_bf16;
     g.B1 = {w, L->ldI, 1, w_batched ? (long long)L->O * L->ldI : 0};
+    if (lrt && lrt_split(m, 1)) {
+      // Split LRT forward: mean product first (plain fp32 store), then the variance GEMM whose single
+      // TMEM accumulator is double-buffered, so the Philox / rsqrt / three-tensor epilogue of tile i runs
+      // under the MMAs of tile i+1 (the dual-accumulator kernel fills all 512 TMEM columns and cannot).
+      EpiParams p0;
+      memset(&p0, 0, sizeof(p0));
+      p0.M = N; p0.N = L->O;
+      p0.out_f32 = m->aux; p0.ld_f32 = m->ld_aux; p0.zs_f32 = (long long)N * m->ld_aux;
+      VB_TRY(tc_gemm(m->ctx, EPI_STORE, g, p0, EPI_FWD_LRT));
+      g.A1 = {(const bf16*)m->act2[j], ldi, 1, zs_in};
+      g.B1 = {L->s2_bf16, L->ldI, 1, 0};
+      p.aux = m->aux; p.ld_aux = m->ld_aux; p.zs_aux = (long long)N * m->ld_aux;
+      return tc_gemm(m->ctx, EPI_FWD_LRT2, g, p, EPI_FWD_LRT);
+    }
     if (lrt) {
       g.A2 = {(const bf16*)m->act2[j], ldi, 1, zs_in};
       g.B2 = {L->s2_bf16, L->ldI, 1, 0};
@@ -182,11 +205,25 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
       g.M = N; g.N = L->I; g.K = L->O; g.batch = Zrun;
       g.A1 = {(const bf16*)m->G[j], ldo, 1, zs_out};
       g.B1 = {lrt ? L->mu_bf16 : L->w_bf16, L->ldI, 0, w_batched ? (long long)L->O * L->ldI : 0};
+      if (lrt && lrt_split(m, 2)) {
+        // split LRT backward-data: T = H s2 first, then G mu with the 2 X .* T join in its epilogue
+        TcGemmArgs g1 = g;
+        g1.A1 = {(const bf16*)m->H[j], ldo, 1, zs_out};
+        g1.B1 = {L->s2_bf16, L->ldI, 0, 0};
+        EpiParams p0;
+        memset(&p0, 0, sizeof(p0));
+        p0.M = N; p0.N = L->I;
+        p0.out_f32 = m->aux; p0.ld_f32 = m->ld_aux; p0.zs_f32 = (long long)N * m->ld_aux;
+        VB_TRY(tc_gemm(m->ctx, EPI_STORE, g1, p0, EPI_DX_LRT));
+        p.aux = m->aux; p.ld_aux = m->ld_aux; p.zs_aux = (long long)N * m->ld_aux;
+        VB_TRY(tc_gemm(m->ctx, EPI_DX_LRT2, g, p, EPI_DX_LRT));
+      } else {
       if (lrt) {
         g.A2 = {(const bf16*)m->H[j], ldo, 1, zs_out};
         g.B2 = {L->s2_bf16, L->ldI, 0, 0};
       }
       VB_TRY(tc_gemm(m->ctx, mode, g, p));
+      }
     } else {
       SimtGemmArgs g;
       memset(&g, 0, sizeof(g));
@@ -468,6 +505,12 @@ extern "C" int vbnn_mlp_create(vbnn_ctx* ctx, const int* sizes, int n_sizes, int
     A_(&m->G[j], bytes);
     if (m->lrt && vb) { A_(&m->R[j], bytes); A_(&m->H[j], bytes); }
   }
+  if (m->lrt && m->bf16) {
+    int mx = 0;
+    for (int k = 0; k < n_sizes; ++k) mx = m->ld[k] > mx ? m->ld[k] : mx;
+    m->ld_aux = mx;
+    A_((void**)&m->aux, ZN * (size_t)mx * 4);
+  }
   m->ld_logits = m->ld[Lc];
   A_((void**)&m->logits, ZN * m->ld_logits * 4);
   A_((void**)&m->targets, (size_t)max_batch * 4);
@@ -518,6 +561,7 @@ extern "C" int vbnn_mlp_destroy(vbnn_mlp* m) {
   for (void* p : m->R) if (p) cudaFree(p);
   for (void* p : m->G) if (p) cudaFree(p);
   for (void* p : m->H) if (p) cudaFree(p);
+  if (m->aux) cudaFree(m->aux);
   if (m->logits) cudaFree(m->logits);
   if (m->logp) cudaFree(m->logp);
   if (m->targets) cudaFree(m->targets);

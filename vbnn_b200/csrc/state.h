@@ -109,6 +109,7 @@ struct vbnn_mlp {
   // activations, element type float (FP32) or bf16 (BF16); index k = features sizes[k]
   std::vector<void*> act, act2;      // act[0] = staged input [N x ld0]; act[k>0] = [Z x N x ld_k]
   std::vector<void*> R, G, H;        // per layer output k+1: [Z x N x ld_{k+1}]
+  float* aux = nullptr; int ld_aux = 0;     // fp32 [Z x N x ld_aux]: first product of the split LRT GEMMs
   float* logits = nullptr; int ld_logits = 0;
   float* logp = nullptr;
   float* targets = nullptr;          // staged targets [N]
@@ -148,7 +149,8 @@ int peer_wait_params(vbnn_mlp* m);                                        // mai
 int peer_after_dw(vbnn_mlp* m, int j);                                    // signal + owner update + push
 int peer_check(vbnn_mlp* m);                                              // host: a peer wait timed out?
 // tensor-core GEMM launch with optional event bracketing (ctx->profiling)
-int tc_gemm(vbnn_ctx* ctx, int mode, const TcGemmArgs& g, const EpiParams& p);
+// prof_cls: class the launch is accounted under (default: its mode)
+int tc_gemm(vbnn_ctx* ctx, int mode, const TcGemmArgs& g, const EpiParams& p, int prof_cls = -1);
 int prof_collect(vbnn_ctx* ctx);
 int prof_mark(vbnn_ctx* ctx, int id);     // id 0 starts a minibatch; no-op unless profiling
 }  // namespace vbnn
