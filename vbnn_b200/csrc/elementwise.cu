@@ -286,7 +286,6 @@ __global__ void __launch_bounds__(TPB, TPB == 128 ? 6 : 1) k_update(UpdateParams
       const size_t idx = (p.partials_pingpong ? (size_t)((t_now + 1) & 1) * kMaxPartials : 0) + p.part_off + blockIdx.x;
       p.next_partials[idx] = r;
       for (int q = 0; q < p.n_peer; ++q) p.peer_partials[q][idx] = r;
-      for (int z = blockIdx.x + gridDim.x; z < p.zero_fill_to; z += gridDim.x) p.next_partials[idx - blockIdx.x + z] = 0.0;
     }
   }
   if (STATS) {

@@ -67,10 +67,10 @@ struct UpdateParams {
   // other ranks; pointers pre-offset like their local counterparts, nullptr = not pushed
   int n_push;
   bf16* push_mu16[7]; bf16* push_s216[7]; float* push_mu[7]; float* push_lv[7]; float* push_s2[7];
-  // ---- co-resident variant: 128-thread blocks with <= 80 registers, one per SM, that fit beside a
-  // resident tcgen05 GEMM CTA, so the HBM-bound update overlaps the tensor-bound backward GEMMs ----
+  // ---- co-resident variant (peer mode, layers > 0): 128-thread blocks with <= 80 registers, one per SM,
+  // that fit beside a resident tcgen05 GEMM CTA, so a shard's update starts while the persistent GEMMs
+  // of the layers below own every SM ----
   int coresident;
-  int zero_fill_to;                     // > grid: entries [grid, zero_fill_to) of next_partials are zeroed
 };
 int launch_update(const UpdateParams& p, int* grid_out, cudaStream_t st);
 

@@ -188,9 +188,9 @@ static void fill_noise(vbnn_layer* L, EpiParams& p, uint32_t kind, const float* 
   p.row0 = 0;
 }
 
-int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t, cudaStream_t stream, bool coresident) {
+int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
   vbnn_ctx* c = L->ctx;
-  cudaStream_t st = stream ? stream : c->stream;
+  cudaStream_t st = c->stream;
   const long long W = (long long)L->O * L->I;
   if (L->kind == VBNN_KIND_LINEAR) {
     // optim.sgd over the whole output layer (mlp.lua:120-123; quirk Q4: intent, not the 110 slice)
@@ -218,14 +218,9 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t, cudaStr
   u.lrt = is_lrt(L);
   double* stat_dev = stats ? c->d_partials + kMaxPartials : nullptr;
   u.stat_partials = stat_dev;
-  if (coresident && !stats && (L->I & 3) == 0) {
-    u.coresident = 1;
-    u.grid_override = kNumSMs < L->n_part ? kNumSMs : L->n_part;
-    u.zero_fill_to = L->n_part;
-  }
   int grid = 0;
   cudaEvent_t pa = nullptr, pb = nullptr;
-  const bool timed = c->profiling && st == c->stream;
+  const bool timed = c->profiling;
   if (timed) {
     // bench.py's HBM roofline: class 7 = fused update, "flops" slot = algorithmic bytes (56 B / weight)
     for (cudaEvent_t* e : {&pa, &pb}) {
@@ -401,7 +396,6 @@ extern "C" int vbnn_ctx_destroy(vbnn_ctx* c) {
   if (c->h_partials) cudaFreeHost(c->h_partials);
   if (c->h_scalars) cudaFreeHost(c->h_scalars);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-  if (c->side_stream) cudaStreamDestroy(c->side_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return VBNN_OK;

@@ -308,7 +308,7 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
 // reduce_overlap: data-parallel step -- the allreduce of layer j's {gW, gS, gb} slice starts on the
 // communication stream as soon as its dW is done and overlaps the backward of the layers below.
 int run_samples(vbnn_mlp* m, int N, int Zrun, int sample0, int accumulate, bool backward, bool reduce_overlap = false,
-                bool peer = false, bool side_update = false) {
+                bool peer = false) {
   const int Lc = nlayers(m);
   vbnn_ctx* c = m->ctx;
   for (int j = 0; j < Lc; ++j) VB_TRY(forward_layer(m, j, N, Zrun, sample0, false));
@@ -322,14 +322,6 @@ int run_samples(vbnn_mlp* m, int N, int Zrun, int sample0, int accumulate, bool 
       // peer mode: signal, then the owner update + all-gather of layer j run on the side stream while
       // this stream continues with the layers below
       if (peer) VB_TRY(peer_after_dw(m, j));
-      // single GPU: the HBM-bound update of layer j > 0 runs on the side stream in small co-resident CTAs
-      // beside the tensor-bound GEMMs of the layers below (layer 0 has nothing left to hide behind)
-      if (side_update && j > 0) {
-        VB_CUDA(cudaEventRecord(m->ev_bwd[j], c->stream));
-        VB_CUDA(cudaStreamWaitEvent(c->side_stream, m->ev_bwd[j], 0));
-        VB_TRY(layer_update_internal(m->layers[j], nullptr, false, c->side_stream, true));
-        VB_CUDA(cudaEventRecord(m->ev_red[j], c->side_stream));
-      }
       if (reduce_overlap) {
         VB_CUDA(cudaEventRecord(m->ev_bwd[j], c->stream));
         VB_CUDA(cudaStreamWaitEvent(c->comm_stream, m->ev_bwd[j], 0));
@@ -340,15 +332,9 @@ int run_samples(vbnn_mlp* m, int N, int Zrun, int sample0, int accumulate, bool 
   return VBNN_OK;
 }
 
-int update_all(vbnn_mlp* m, bool wait_reduce = false, bool side_update = false) {
+int update_all(vbnn_mlp* m, bool wait_reduce = false) {
   const int Lc = nlayers(m);
   cudaStream_t st = m->ctx->stream;
-  if (side_update) {
-    // layers > 0 were updated on the side stream during backward: update layer 0 here, then join
-    VB_TRY(layer_update_internal(m->layers[0], nullptr, false));
-    for (int j = 1; j < Lc; ++j) VB_CUDA(cudaStreamWaitEvent(st, m->ev_red[j], 0));
-    return VBNN_OK;
-  }
   // mlp.lua:117-142: SGD on the output layer first, then the VB layers.  The layers are independent,
   // so with the overlapped allreduce they are updated top-down, each as soon as its reduction lands.
   if (m->layers[Lc - 1]->kind == VBNN_KIND_LINEAR) {
@@ -395,12 +381,9 @@ int step_body(vbnn_mlp* m, int N) {
   static int ov_env = -1;
   if (ov_env < 0) { const char* e = getenv("VBNN_DP_OVERLAP"); ov_env = e ? atoi(e) : 1; }
   const bool overlap = dp && ov_env && m->ctx->comm_stream != nullptr;
-  static int su_env = -1;
-  if (su_env < 0) { const char* e = getenv("VBNN_UPDATE_OVERLAP"); su_env = e ? atoi(e) : 0; }
-  const bool side_update = !dp && su_env && m->bf16 && m->ctx->side_stream != nullptr && nlayers(m) > 1;
-  VB_TRY(run_samples(m, N, m->Z, 0, /*accumulate=*/0, true, overlap, false, side_update));     // :34
+  VB_TRY(run_samples(m, N, m->Z, 0, /*accumulate=*/0, true, overlap));                         // :34
   if (dp && !overlap) VB_TRY(comm_allreduce_internal(m->ctx, m->grad_arena, m->grad_count, st));
-  VB_TRY(update_all(m, overlap, side_update));                                                 // :40
+  VB_TRY(update_all(m, overlap));                                                              // :40
   VB_TRY(prof_mark(m->ctx, 6));
   VB_TRY(launch_finalize_result(m->result_acc, m->Z, N, m->result, st));                       // :38-39
   VB_TRY(launch_bump(m->ctx->d_step, m->t_list_dev, m->n_t, st));
@@ -533,11 +516,6 @@ extern "C" int vbnn_mlp_create(vbnn_ctx* ctx, const int* sizes, int n_sizes, int
     if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) { r = VBNN_E_CUDA; break; }
     m->ev_bwd.push_back(a); m->ev_red.push_back(b);
-  }
-  if (r == VBNN_OK && !ctx->side_stream) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if (cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, hi) != cudaSuccess) r = VBNN_E_CUDA;
   }
   const char* env = getenv("VBNN_NO_GRAPH");
   if (env && env[0] == '1') m->use_graph = false;

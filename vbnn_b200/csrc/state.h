@@ -32,7 +32,6 @@ struct vbnn_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, nranks = 1;
   cudaStream_t comm_stream = nullptr;   // per-layer gradient allreduce overlaps the rest of backward
-  cudaStream_t side_stream = nullptr;   // single GPU: co-resident updates of the upper layers overlap the backward GEMMs
 };
 
 struct vbnn_layer {
@@ -135,8 +134,7 @@ struct vbnn_mlp {
 namespace vbnn {
 int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts* opts, int S_alloc,
                           float* gW, float* gS, float* gb, int id, vbnn_layer** out);
-int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t, cudaStream_t stream = nullptr,
-                          bool coresident = false);
+int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t);
 int layer_refresh_copies(vbnn_layer* L);
 int layer_compute_prior_internal(vbnn_layer* L);
 int layer_refresh_prior_partials(vbnn_layer* L);
