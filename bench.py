@@ -355,7 +355,7 @@ def main():
     roof = None
     upd = prof.pop("update", None)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01c_c3_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01e_c3_traffic.json")
     if args.workload == "c3" and os.path.exists(tpath):
         tj = json.load(open(tpath))
         traffic = dict(gemm_bytes_per_launch=tj["gemm_traffic_bytes_per_launch"], source=tj["source"])
