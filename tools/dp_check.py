@@ -64,6 +64,9 @@ def main():
             dist.barrier()
         dp = [m.means.clone() for m in net.model[:-1]] + [net.model[-1].weight.clone()]
         dp_lv = [m.lvars.clone() for m in net.model[:-1]]
+        from vbnn_b200 import _lib as VL
+        adam_ids = (VL.BUF_ADAM_M_MU, VL.BUF_ADAM_V_MU, VL.BUF_ADAM_M_VAR, VL.BUF_ADAM_V_VAR)
+        dp_adam = [[m.get(b) for b in adam_ids] for m in net.model[:-1]]     # needs sync_replicas in peer mode
         # all ranks must hold identical parameters
         for t in dp:
             ref = t.clone(); dist.broadcast(ref, 0)
@@ -84,6 +87,12 @@ def main():
             for a, m in zip(dp_lv, one.model[:-1]):
                 e = float((a - m.lvars).norm() / m.lvars.norm())
                 ok &= e < tol
+            for bufs, m in zip(dp_adam, one.model[:-1]):                       # optimiser state of every shard
+                for a, b in zip(bufs, adam_ids):
+                    r = m.get(b)
+                    e = float((a - r).norm() / max(float(r.norm()), 1e-30))
+                    ok &= e < 10 * tol
+            assert all(m.t == 3 for m in net.model)
             torch.cuda.set_stream(ctx_dp.stream)
         ctx_dp.synchronize(); dist.barrier()          # nobody still writes into a peer's buffers
         del net
