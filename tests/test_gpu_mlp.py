@@ -402,3 +402,59 @@ def test_convnet_head_behind_the_same_abi(ctx):
     before = cpu(h1.means).copy()
     h1.update(opt); h2.update(opt)                         # convnet.lua:105-117
     assert not np.array_equal(cpu(h1.means), before)
+
+
+def test_c3_exact_size_properties(ctx):
+    """BASELINE configs[2] at its exact size (4096-4096x4-1000, batch 8192, local reparameterisation): too big
+    for the CPU oracle in seconds, so size-independent properties through the same C ABI --
+    (1) the bf16 tcgen05 path against this library's fp32 CUDA-core path (itself oracle-checked at small
+        sizes above) with identical Philox noise: loss <= 2e-2, gradients <= 0.12 / 0.15, means <= 2e-2;
+    (2) counter-based noise makes the minibatch reproducible: re-running it from the same parameters and
+        step counter gives bit-identical gradWeight / gradSum (no atomics on that path);
+    (3) the loss of a freshly initialised net on random labels is close to log(1000) + the LRT noise term
+        and finite everywhere."""
+    import vbnn_b200
+    sizes, N = [4096, 4096, 4096, 4096, 4096, 1000], 8192
+    g = torch.Generator().manual_seed(3)
+    X = torch.randn(N, sizes[0], generator=g).cuda()
+    T = torch.randint(1, sizes[-1] + 1, (N,), generator=g).float().cuda()
+    res = {}
+    for precision in ("fp32", "bf16"):
+        opt = vbnn_b200.default_opt(input_size=sizes[0], hidden=sizes[1:-1], classes=[str(i) for i in range(sizes[-1])],
+                                    S=1, B=100.0, batchSize=N, testBatchSize=N, mu_init=1, var_init=0.001,
+                                    reparam="local", precision=precision, strict_reference=False, log=False, seed=5)
+        net = vbnn_b200.MLP(opt, ctx, max_batch=N)
+        net.init_params(seed=4, he_means=True)
+        ctx.set_step(21)
+        err, acc = net.train_step(X, T)
+        assert math.isfinite(err) and 0.0 <= acc <= 100.0
+        gw = [m.gradWeight.clone() for m in net.model]
+        gs = [m.gradSum.clone() for m in net.model[:-1]]
+        mu = [m.means.clone() for m in net.model[:-1]]
+        for t in gw + gs + mu:
+            assert bool(torch.isfinite(t).all())
+        res[precision] = (err, gw, gs, mu)
+        if precision == "bf16":
+            # (2) same parameters + same step counter -> same minibatch, bit for bit
+            net2 = vbnn_b200.MLP(opt, ctx, max_batch=N)
+            net2.init_params(seed=4, he_means=True)
+            ctx.set_step(21)
+            err2, _ = net2.train_step(X, T)
+            assert abs(err2 - err) < 1e-5 * abs(err)       # the loss sum itself is an atomic accumulation
+            for a, m in zip(gw, net2.model):
+                assert torch.equal(a, m.gradWeight)
+            for a, m in zip(gs, net2.model[:-1]):
+                assert torch.equal(a, m.gradSum)
+            del net2
+        del net
+        torch.cuda.empty_cache()
+    e32, e16 = res["fp32"][0], res["bf16"][0]
+    assert abs(e16 - e32) < 2e-2 * abs(e32), (e16, e32)
+    assert e32 > 0.8 * math.log(1000.0)
+    relt = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
+    for a, b in zip(res["bf16"][1], res["fp32"][1]):
+        assert relt(a, b) < 0.12
+    for a, b in zip(res["bf16"][2], res["fp32"][2]):
+        assert relt(a, b) < 0.15
+    for a, b in zip(res["bf16"][3], res["fp32"][3]):
+        assert relt(a, b) < 2e-2
