@@ -34,10 +34,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(kThreads) k_sample_w(SampleParams p) {
   const int Q = (p.I + 3) >> 2;
   const long long quads = (long long)p.O * Q;
-  const int s = blockIdx.y;
-  PhiloxStream ps = p.ps;
-  ps.sample += (uint32_t)s;
-  if (p.step_ptr) ps.step = *p.step_ptr;
+  PhiloxStream ps0 = p.ps;
+  if (p.step_ptr) ps0.step = *p.step_ptr;
   const long long OI = (long long)p.O * p.I;
   for (long long qd = blockIdx.x * (long long)blockDim.x + threadIdx.x; qd < quads;
        qd += (long long)gridDim.x * blockDim.x) {
@@ -45,49 +43,57 @@ __global__ void __launch_bounds__(kThreads) k_sample_w(SampleParams p) {
     const int i0 = c * 4;
     const long long e0 = (long long)o * p.I + i0;
     const int nv = min(4, p.I - i0);
-    float mu[4], sg[4], ep[4], w[4];
+    // mu and sigma are read (and sigma exponentiated) once for ALL samples of the minibatch
+    float mu[4], sd[4];
     if (VEC) {
       float4 a = ld4(p.mu + e0), b = ld4(p.sig + e0);
       mu[0] = a.x; mu[1] = a.y; mu[2] = a.z; mu[3] = a.w;
-      sg[0] = b.x; sg[1] = b.y; sg[2] = b.z; sg[3] = b.w;
+      sd[0] = b.x; sd[1] = b.y; sd[2] = b.z; sd[3] = b.w;
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         mu[j] = j < nv ? p.mu[e0 + j] : 0.f;
-        sg[j] = j < nv ? p.sig[e0 + j] : 0.f;
+        sd[j] = j < nv ? p.sig[e0 + j] : 0.f;
       }
     }
-    if (p.eps_in) {
-      if (VEC) {
-        float4 e = ld4(p.eps_in + s * OI + e0);
-        ep[0] = e.x; ep[1] = e.y; ep[2] = e.z; ep[3] = e.w;
+    if (p.sig_is_lvar) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sd[j] = __expf(0.5f * sd[j]);
+    }
+#pragma unroll 2
+    for (int s = blockIdx.y; s < p.S; s += gridDim.y) {
+      float ep[4], w[4];
+      if (p.eps_in) {
+        if (VEC) {
+          float4 e = ld4(p.eps_in + s * OI + e0);
+          ep[0] = e.x; ep[1] = e.y; ep[2] = e.z; ep[3] = e.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ep[j] = j < nv ? p.eps_in[s * OI + e0 + j] : 0.f;
+        }
       } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ep[j] = j < nv ? p.eps_in[s * OI + e0 + j] : 0.f;
+        PhiloxStream ps = ps0;
+        ps.sample += (uint32_t)s;
+        philox_normal4(ps, (uint32_t)qd, ep);
       }
-    } else {
-      philox_normal4(ps, (uint32_t)qd, ep);
-    }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float sd = p.sig_is_lvar ? __expf(0.5f * sg[j]) : sg[j];
-      w[j] = fmaf(sd, ep[j], mu[j]);                      // VBLinear.lua:59
-    }
-    if (p.eps_out) {
-      if (VEC) st4(p.eps_out + s * OI + e0, make_float4(ep[0], ep[1], ep[2], ep[3]));
-      else
-        for (int j = 0; j < nv; ++j) p.eps_out[s * OI + e0 + j] = ep[j];
-    }
-    if (p.w_f32) {
-      if (VEC) st4(p.w_f32 + s * OI + e0, make_float4(w[0], w[1], w[2], w[3]));
-      else
-        for (int j = 0; j < nv; ++j) p.w_f32[s * OI + e0 + j] = w[j];
-    }
-    if (p.w_bf16) {
-      bf16* dst = p.w_bf16 + s * p.zs_bf16 + (long long)o * p.ld_bf16 + i0;
-      if (nv == 4) st4_bf16(dst, w[0], w[1], w[2], w[3]);
-      else
-        for (int j = 0; j < nv; ++j) dst[j] = __float2bfloat16_rn(w[j]);
+      for (int j = 0; j < 4; ++j) w[j] = fmaf(sd[j], ep[j], mu[j]);          // VBLinear.lua:59
+      if (p.eps_out) {
+        if (VEC) st4(p.eps_out + s * OI + e0, make_float4(ep[0], ep[1], ep[2], ep[3]));
+        else
+          for (int j = 0; j < nv; ++j) p.eps_out[s * OI + e0 + j] = ep[j];
+      }
+      if (p.w_f32) {
+        if (VEC) st4(p.w_f32 + s * OI + e0, make_float4(w[0], w[1], w[2], w[3]));
+        else
+          for (int j = 0; j < nv; ++j) p.w_f32[s * OI + e0 + j] = w[j];
+      }
+      if (p.w_bf16) {
+        bf16* dst = p.w_bf16 + s * p.zs_bf16 + (long long)o * p.ld_bf16 + i0;
+        if (nv == 4) st4_bf16(dst, w[0], w[1], w[2], w[3]);
+        else
+          for (int j = 0; j < nv; ++j) dst[j] = __float2bfloat16_rn(w[j]);
+      }
     }
   }
 }
@@ -446,11 +452,34 @@ __global__ void __launch_bounds__(kThreads) k_loss(LossParams p) {
         my_corr = (arg == tgt) ? 1.f : 0.f;
       }
     }
-    // rows of one block almost always share z; fall back to per-warp atomics otherwise
-    if (lane == 0 && r < rows) {
-      atomicAdd(p.result + 2 * (p.z_slot0 + z), my_loss);
-      atomicAdd(p.result + 2 * (p.z_slot0 + z) + 1, my_corr);
+    // One atomic pair per block instead of per row (8192 rows hammering two addresses serialised the
+    // whole kernel): the rows of one block almost always share z; per-warp atomics otherwise.
+    __shared__ float sh_loss[kThreads / 32], sh_corr[kThreads / 32];
+    __shared__ int sh_z[kThreads / 32];
+    const int w = threadIdx.x >> 5;
+    if (lane == 0) { sh_loss[w] = my_loss; sh_corr[w] = my_corr; sh_z[w] = r < rows ? z : -1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int z0 = -1; bool same = true;
+      for (int k = 0; k < warps_per_block; ++k) {
+        if (sh_z[k] < 0) continue;
+        if (z0 < 0) z0 = sh_z[k];
+        same &= sh_z[k] == z0;
+      }
+      if (same && z0 >= 0) {
+        float a = 0.f, c = 0.f;
+        for (int k = 0; k < warps_per_block; ++k) if (sh_z[k] >= 0) { a += sh_loss[k]; c += sh_corr[k]; }
+        atomicAdd(p.result + 2 * (p.z_slot0 + z0), a);
+        atomicAdd(p.result + 2 * (p.z_slot0 + z0) + 1, c);
+      } else {
+        for (int k = 0; k < warps_per_block; ++k)
+          if (sh_z[k] >= 0) {
+            atomicAdd(p.result + 2 * (p.z_slot0 + sh_z[k]), sh_loss[k]);
+            atomicAdd(p.result + 2 * (p.z_slot0 + sh_z[k]) + 1, sh_corr[k]);
+          }
+      }
     }
+    __syncthreads();
   }
 }
 
@@ -612,7 +641,10 @@ __global__ void __launch_bounds__(kThreads) k_snr(const float* mu, const float* 
 // ------------------------------------------------------------------ launchers -----------
 int launch_sample_w(const SampleParams& p, cudaStream_t st) {
   const long long quads = (long long)p.O * ((p.I + 3) / 4);
-  dim3 grid(grid_for(quads), p.S);
+  // enough quads to fill the GPU: one thread draws all S samples of its quad; small layers spread the
+  // samples over grid.y instead
+  const int gx = grid_for(quads);
+  dim3 grid(gx, gx >= kNumSMs * 4 ? 1 : p.S);
   if ((p.I & 3) == 0) k_sample_w<true><<<grid, kThreads, 0, st>>>(p);
   else k_sample_w<false><<<grid, kThreads, 0, st>>>(p);
   VB_CUDA(cudaGetLastError());

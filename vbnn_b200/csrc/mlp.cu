@@ -285,6 +285,12 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
         g.A2 = {(const bf16*)m->H[j], ldo, 0, zs_out};
         g.B2 = {(const bf16*)m->act2[j], ldi, 0, zs_in};
       }
+      if (L->kind == VBNN_KIND_LINEAR && Zrun > 1 && zs_in == (long long)N * ldi) {
+        // plain nn.Linear (no per-sample epsilon): sum_z G_z^T X_z is ONE GEMM over K = Z * N rows, the
+        // samples being contiguous in both operands -- no per-sample accumulator round trips
+        g.K = N * Zrun; g.batch = 1;
+        g.A1.zs = 0; g.B1.zs = 0;
+      }
       VB_TRY(tc_gemm(m->ctx, mode, g, p));
     } else {
       SimtGemmArgs g;
