@@ -286,12 +286,14 @@ __global__ void __launch_bounds__(TPB, TPB == 128 ? 6 : 1) k_update(UpdateParams
       }
     }
   }
+  if (p.n_push > 0 || p.n_peer > 0) __threadfence_system();   // peer stores of this thread are out before the flag kernel
   if (p.next_partials) {
     double r = block_sum((double)nxt, sh);
     if (threadIdx.x == 0) {
       const size_t idx = (p.partials_pingpong ? (size_t)((t_now + 1) & 1) * kMaxPartials : 0) + p.part_off + blockIdx.x;
       p.next_partials[idx] = r;
       for (int q = 0; q < p.n_peer; ++q) p.peer_partials[q][idx] = r;
+      if (p.n_peer > 0) __threadfence_system();
     }
   }
   if (STATS) {

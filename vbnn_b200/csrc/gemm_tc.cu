@@ -600,6 +600,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     }
   }
 
+  // peer mode: this CTA's gradient tiles went to other GPUs; make them visible system-wide before the
+  // kernel retires (the flag that announces them is raised by a later kernel of the same stream)
+  if constexpr (ZACC) { if (p.scatter_rows) __threadfence_system(); }
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {

@@ -53,6 +53,13 @@ static inline bool is_lrt(const vbnn_layer* L) {
   return L->kind == VBNN_KIND_VB && L->opts.reparam == VBNN_REPARAM_LOCAL;
 }
 static inline size_t esz(const vbnn_layer* L) { return is_bf16(L) ? 2 : 4; }
+// peer mode: mu / log sigma^2 of rows owned by other ranks are only kept current when the forward pass
+// needs them in fp32 (weight sampling); otherwise whole-layer reads need vbnn_mlp_sync_replicas first
+static int check_params_fresh(const vbnn_layer* L, const char* what) {
+  VB_CHECK(!(L->shard_stale && *L->shard_stale && is_lrt(L)), VBNN_E_STATE,
+           "%s in peer mode: rows owned by other ranks are out of date; call vbnn_mlp_sync_replicas on every rank first", what);
+  return VBNN_OK;
+}
 
 int layer_refresh_copies(vbnn_layer* L) {
   cudaStream_t st = L->ctx->stream;
@@ -499,6 +506,7 @@ extern "C" int vbnn_layer_sample(vbnn_layer* L, int sample_idx, const float* eps
 
 extern "C" int vbnn_layer_clamp_to_map(vbnn_layer* L) {
   VB_CHECK(L && L->kind == VBNN_KIND_VB, VBNN_E_INVALID, "vbnn_layer_clamp_to_map: not a VB layer");
+  VB_TRY(check_params_fresh(L, "vbnn_layer_clamp_to_map"));
   cudaStream_t st = L->ctx->stream;
   L->map_mode = true;
   if (is_lrt(L)) {
@@ -657,6 +665,7 @@ extern "C" int vbnn_layer_reset_acc(vbnn_layer* L) {
 
 extern "C" int vbnn_layer_compute_prior(vbnn_layer* L, float* mu_hat, float* var_hat) {
   VB_CHECK(L && L->kind == VBNN_KIND_VB, VBNN_E_INVALID, "vbnn_layer_compute_prior: not a VB layer");
+  VB_TRY(check_params_fresh(L, "vbnn_layer_compute_prior"));
   VB_TRY(layer_compute_prior_internal(L));
   cudaStream_t st = L->ctx->stream;
   VB_CUDA(cudaMemcpyAsync(L->ctx->h_scalars, L->var_hat_dev, 4, cudaMemcpyDeviceToHost, st));
@@ -682,6 +691,7 @@ extern "C" int vbnn_layer_update(vbnn_layer* L, vbnn_stats* stats) {
 
 extern "C" int vbnn_layer_calc_lc(vbnn_layer* L, float* lc_dev, float* sum_host) {
   VB_CHECK(L && L->kind == VBNN_KIND_VB, VBNN_E_INVALID, "vbnn_layer_calc_lc: not a VB layer");
+  VB_TRY(check_params_fresh(L, "vbnn_layer_calc_lc"));
   vbnn_ctx* c = L->ctx;
   cudaStream_t st = c->stream;
   const long long W = (long long)L->O * L->I;
@@ -801,6 +811,7 @@ extern "C" int vbnn_layer_set_t(vbnn_layer* L, int t) {
 
 extern "C" int vbnn_layer_snr_count(vbnn_layer* L, float thresh, uint8_t* mask_dev, long long* count) {
   VB_CHECK(L && L->kind == VBNN_KIND_VB, VBNN_E_INVALID, "vbnn_layer_snr_count: not a VB layer");
+  VB_TRY(check_params_fresh(L, "vbnn_layer_snr_count"));
   vbnn_ctx* c = L->ctx;
   unsigned long long* cnt = reinterpret_cast<unsigned long long*>(c->d_partials);
   VB_CUDA(cudaMemsetAsync(cnt, 0, 8, c->stream));
