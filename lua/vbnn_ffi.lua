@@ -33,6 +33,27 @@ int vbnn_layer_grads(vbnn_layer*, float* mleg, float* mlcg, float* vleg, float* 
 int vbnn_layer_update(vbnn_layer*, vbnn_stats*);
 int vbnn_layer_calc_lc(vbnn_layer*, float* lc_dev, float* sum_host);
 int vbnn_layer_device_ptr(vbnn_layer*, int which, float** ptr_dev, size_t* count);
+/* net level (lua/mlp.lua): the mlp.lua object and the main.lua:19-51 closure */
+typedef struct vbnn_mlp vbnn_mlp;
+int vbnn_mlp_create(vbnn_ctx*, const int* sizes, int n_sizes, int vb_output, int max_batch, const vbnn_opts*, vbnn_mlp** out);
+int vbnn_mlp_destroy(vbnn_mlp*);
+int vbnn_mlp_layer(vbnn_mlp*, int k, vbnn_layer** out);
+int vbnn_mlp_init_params(vbnn_mlp*, uint64_t seed, int he_means);
+int vbnn_mlp_reset_gradients(vbnn_mlp*);
+int vbnn_mlp_sample(vbnn_mlp*, int sample_idx);
+int vbnn_mlp_run(vbnn_mlp*, const float* X_dev, const float* targets_dev, int N, int sample_idx, float* err_host, float* acc_host);
+int vbnn_mlp_update(vbnn_mlp*);
+int vbnn_mlp_calc_lc(vbnn_mlp*, float* lc_host);
+int vbnn_mlp_step(vbnn_mlp*, const float* X_dev, const float* targets_dev, int N, float* result_dev);
+int vbnn_mlp_submit_host(vbnn_mlp*, const float* X_host, const float* targets_host, int N);
+int vbnn_mlp_collect(vbnn_mlp*, float* err_host, float* acc_host);
+int vbnn_mlp_test(vbnn_mlp*, const float* X_dev, const float* targets_dev, int N, int n_samples, float* err_host, float* acc_host);
+/* data parallel: NCCL id, then (optionally) the peer-memory exchange */
+int vbnn_comm_unique_id(void* id128);
+int vbnn_comm_init(vbnn_ctx*, const void* id128, int rank, int nranks);
+int vbnn_mlp_peer_export(vbnn_mlp*, void* blob, size_t capacity, size_t* blob_len);
+int vbnn_mlp_peer_import(vbnn_mlp*, const void* blobs_all_ranks, size_t blob_len);
+int vbnn_mlp_sync_replicas(vbnn_mlp*);
 ]]
 
 local C = ffi.load('vbnn')
