@@ -63,3 +63,21 @@ def test_python_mirror_has_the_reference_interface():
         assert callable(getattr(vbnn_b200.MLP, name)), name
     opt = vbnn_b200.default_opt()
     assert opt["S"] == 30 and opt["hidden"] == [10] and opt["B"] == 1e6
+
+
+def test_lua_shim_binds_only_exported_symbols():
+    """lua/vbnn_ffi.lua cannot be executed here (no LuaJIT); at least every function its ffi.cdef declares and
+    every C.<name> call in lua/*.lua must be a symbol libvbnn.so exports."""
+    import ctypes
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = ctypes.CDLL(os.path.join(root, "vbnn_b200", "libvbnn.so"))
+    cdef = open(os.path.join(root, "lua", "vbnn_ffi.lua")).read()
+    declared = set(re.findall(r"\b(vbnn_[a-z0-9_]+)\s*\(", cdef))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), name
+    for fn in ("VBLinear.lua", "mlp.lua", "vbnn_ffi.lua"):
+        src = open(os.path.join(root, "lua", fn)).read()
+        for name in set(re.findall(r"\bC\.(vbnn_[a-z0-9_]+)", src)):
+            assert name in declared, (fn, name)
