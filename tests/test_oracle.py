@@ -217,3 +217,50 @@ def test_train_minibatch_runs_and_learns():
         first = first if first is not None else err
         last = err
     assert last < first
+
+
+def test_inherited_torch7_pieces_match_torch_autograd():
+    """The un-vendored Torch7 modules the path inherits (nn.Linear, nn.LogSoftMax, nn.ClassNLLCriterion with
+    sizeAverage, nn.ReLU) are restated by hand in the oracle; pin those restatements to torch's own
+    implementations and autograd (fp64)."""
+    import torch.nn.functional as F
+    rng = np.random.RandomState(2)
+    N, I, C = 9, 7, 5
+    lin = O.LinearOracle(I, C, torch.float64, rng=rng)
+    x = torch.from_numpy(rng.randn(N, I))
+    t1 = torch.from_numpy(rng.randint(1, C + 1, N).astype(np.float64))          # 1-based targets (data.lua:16)
+    # forward
+    y = lin.updateOutput(x)
+    assert torch.allclose(y, F.linear(x, lin.weight, lin.bias), atol=1e-14)
+    logp = O.log_softmax(y)
+    assert torch.allclose(logp, F.log_softmax(y, dim=1), atol=1e-14)
+    loss = O.class_nll_forward(logp, t1)
+    assert abs(loss - float(F.nll_loss(logp, t1.long() - 1))) < 1e-14
+    assert abs(O.get_accuracy(logp, t1) - 100.0 * float((logp.argmax(1) + 1 == t1.long()).double().mean())) < 1e-12
+    # backward through criterion, LogSoftMax and Linear against autograd
+    xa = x.clone().requires_grad_(True)
+    wa = lin.weight.clone().requires_grad_(True)
+    ba = lin.bias.clone().requires_grad_(True)
+    F.nll_loss(F.log_softmax(F.linear(xa, wa, ba), dim=1), t1.long() - 1).backward()
+    g = O.log_softmax_backward(logp, O.class_nll_backward(logp, t1))
+    gx = lin.updateGradInput(x, g)
+    lin.accGradParameters(x, g, 1.0)
+    assert torch.allclose(gx, xa.grad, atol=1e-14)
+    assert torch.allclose(lin.gradWeight, wa.grad, atol=1e-14)
+    assert torch.allclose(lin.gradBias, ba.grad, atol=1e-14)
+    # accGradParameters accumulates and honours `scale` (nn.Linear semantics)
+    lin.accGradParameters(x, g, 0.5)
+    assert torch.allclose(lin.gradWeight, 1.5 * wa.grad, atol=1e-14)
+
+
+def test_sgd_matches_torch_optim():
+    x = torch.arange(6, dtype=torch.float64).reshape(2, 3).clone()
+    g = torch.ones_like(x) * 0.25
+    p = x.clone().requires_grad_(True)
+    opt = torch.optim.SGD([p], lr=1e-3)
+    state = {"learningRate": 1e-3}
+    for _ in range(3):
+        p.grad = g.clone()
+        opt.step()
+        O.optim_sgd(x, g, state)
+    assert torch.allclose(x, p.detach(), atol=1e-15)
