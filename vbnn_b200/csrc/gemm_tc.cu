@@ -222,6 +222,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the reverse: thread t writes its 32 registers to lane (base_lane + t), columns col..col+31
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // ---- UMMA shared-memory descriptor (SWIZZLE_128B) ---------------------------------------------
 // bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
@@ -291,7 +307,10 @@ struct TcCfg {
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int ACC_COLS = NACC * BN;                        // TMEM columns per accumulator stage
   static constexpr int ACC_STAGES = 2 * ACC_COLS <= 512 ? 2 : 1;    // double-buffered when it fits
-  static constexpr int TMEM_COLS = ACC_STAGES * ACC_COLS;
+  // ZACC with BN == 128: columns [256, 384) / [384, 512) hold the running gradWeight / gradSum of the tile
+  // across the Monte-Carlo samples (written by the epilogue warps with tcgen05.st, never by the MMA)
+  static constexpr bool TACC = epi_z_accumulates(MODE) && !DUAL && BN == 128;
+  static constexpr int TMEM_COLS = TACC ? 512 : ACC_STAGES * ACC_COLS;
   // barriers + CLC ring live in the last 512 bytes; the dynamic window is declared 1024-byte aligned, so
   // no alignment slack: together with the 1 KB the system reserves per CTA this leaves room on the SM
   // for one small co-resident CTA of an HBM-bound kernel (the fused update overlaps the backward GEMMs)
@@ -472,7 +491,93 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       decode_tile(sh, tile, mi, ni);
       const int m0 = mi * (BM * CG) + rank * BM, n0 = ni * BN;
       const int row = m0 + q * 32 + lane;
-      if constexpr (ZACC && BN == 64) {
+      if (C::TACC && zn > 1) {
+        // Multi-sample dW with TMEM-RESIDENT accumulators: a 128 x 128 tile (half the operand traffic per MAC
+        // of the 128 x 64 register-accumulating form, which is L2-bandwidth-bound), each warp owning two
+        // 32 x 32 chunks whose running gradWeight / gradSum live in spare TMEM columns between samples --
+        // tcgen05.ld the sample's product, fold it in, tcgen05.st it back; global memory once per tile.
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t tW = tmem_base + lane_base + 256u, tS = tmem_base + lane_base + 384u;
+        const uint32_t qn = (uint32_t)((p.N + 3) >> 2);
+        for (int z = zb; z < zb + zn; ++z) {
+          const bool first = z == zb, last = z + 1 == zb + zn;
+          mbar_wait(tfull_bar(as), aphase);
+          tc_fence_after();
+          const uint32_t tz = tmem_base + lane_base + as * C::ACC_COLS;
+          PhiloxStream psz = ps;
+          psz.sample += (uint32_t)z;
+#pragma unroll 1
+          for (int c = half; c < BN / 32; c += EPIW / 4) {
+            const int col0 = n0 + c * 32;
+            if (col0 >= sh.N) break;                       // warp-uniform
+            const int row0 = m0 + q * 32;
+            const bool full = sh.staged && col0 + 32 <= sh.N;
+            const int rows_valid = min(32, p.M - row0);
+            float *gWd, *gSd;
+            dw_dest(p, row0, gWd, gSd);
+            auto emit = [&](float* dst, float (&a)[32]) {   // the tile's final value of one accumulator -> global
+              const long long goff = (long long)row0 * p.ld_g + col0;
+              if (full) {
+                if (p.accumulate) {
+                  float t[32];
+                  get_tile_f32(my_stage, lane, dst + goff, p.ld_g, rows_valid, t);
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) a[j] += t[j];
+                }
+                put_tile_f32(my_stage, lane, dst + goff, p.ld_g, rows_valid, a);
+              } else if (row < p.M) {
+                const bool vec_g = (p.ld_g & 3) == 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int cq = col0 + 4 * j;
+                  if (cq >= p.N) break;
+                  const int nvalid = min(4, p.N - cq);
+                  float* gp = dst + (long long)row * p.ld_g + cq;
+                  float w4[4] = {a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]};
+                  if (p.accumulate) { float o[4]; load4<float>(gp, o, nvalid, vec_g); for (int k = 0; k < 4; ++k) w4[k] += o[k]; }
+                  store4<float>(gp, w4, nvalid, vec_g);
+                }
+              }
+            };
+            float v1[32], acc[32];
+            tmem_ld32(tz + c * 32, v1);
+            if (!first && p.gS) tmem_ld32(tS + c * 32, acc);
+            tmem_ld_wait();
+            if (p.gS) {
+              if (first) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float e[4];
+                philox_normal4(psz, (uint32_t)row * qn + (uint32_t)((col0 >> 2) + j), e);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[4 * j + k] += v1[4 * j + k] * e[k];       // VBLinear.lua:115
+              }
+              if (last) emit(gSd, acc); else tmem_st32(tS + c * 32, acc);
+            }
+            if (first) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] = p.scale * v1[j];                     // VBLinear.lua:113
+            } else {
+              tmem_ld32(tW + c * 32, acc);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) acc[j] += p.scale * v1[j];
+            }
+            if (last) emit(gWd, acc); else tmem_st32(tW + c * 32, acc);
+          }
+          if (!last) tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CG == 1) mbar_arrive(tempty_bar(as));
+            else mbar_arrive_remote(tempty_bar(as), 0);
+          }
+          if (++as == AS) { as = 0; aphase ^= 1; }
+        }
+      } else if constexpr (ZACC && BN == 64) {
         // Multi-sample dW (weight-space sampling, S > 1): this warp owns ONE 32 x 32 chunk of the
         // tile and keeps its gradWeight / gradSum values in registers across all samples, so the
         // per-sample work is TMEM load + Philox + FMA; global memory is touched once per tile
@@ -736,6 +841,10 @@ TcChoice choose_cfg(const TcGemmArgs& g) {
   if (!c.cg) { const char* e = getenv("VBNN_TC_CG"); if (e) c.cg = atoi(e); }
   if ((c.bn == 128 || c.bn == 256) && (c.cg == 1 || c.cg == 2) && !(c.bn == 128 && c.cg == 2 && !epi_is_dual(MODE))) return c;
   if (epi_z_accumulates(MODE) && g.batch > 1) {
+    static int tacc = -1;
+    if (tacc < 0) { const char* e = getenv("VBNN_TC_TACC"); tacc = e ? atoi(e) : 1; }
+    // TMEM-resident accumulators: 128 x 128 tiles (1), or 256 x 128 CTA-pair tiles (2) when M allows
+    if (tacc && !epi_is_dual(MODE)) return TcChoice{128, tacc == 2 && g.M >= 256 ? 2 : 1};
     static int z64 = -1;
     if (z64 < 0) { const char* e = getenv("VBNN_TC_DW64"); z64 = e ? atoi(e) : 1; }
     if (z64) return TcChoice{64, 1};
@@ -756,6 +865,9 @@ int launch_any(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
   const TcChoice c = choose_cfg<MODE>(g);
   if constexpr (epi_z_accumulates(MODE)) {
     if (c.bn == 64) return launch_cfg<MODE, 64, 1, AK, BKM>(g, p, st);
+    if constexpr (!epi_is_dual(MODE)) {
+      if (c.bn == 128 && c.cg == 2) return launch_cfg<MODE, 128, 2, AK, BKM>(g, p, st);
+    }
   }
   if constexpr (epi_is_dual(MODE)) {
     // 256 x 128 pair tile: two accumulators use 256 TMEM columns, so the accumulator is double-buffered
