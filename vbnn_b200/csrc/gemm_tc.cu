@@ -5,13 +5,18 @@
 // which reach cublasSgemm in the reference) as ONE warp-specialised persistent kernel:
 //
 //   warp 0        TMA producer   cp.async.bulk.tensor (128B-swizzled boxes) -> smem ring
-//   warp 1        MMA issuer     tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM
-//   warps 2..9    epilogue       tcgen05.ld TMEM -> registers -> fused VB epilogue (epilogue.cuh)
+//   warp 1        MMA issuer     one thread: tcgen05.mma.cta_group::{1,2}.kind::f16, fp32 accumulators in TMEM
+//   warps 2..9    epilogue       tcgen05.ld TMEM -> registers -> fused VB epilogue (epilogue.cuh /
+//                                epilogue_tc.cuh: coalesced I/O through per-warp swizzled smem tiles)
 //
-// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue,
-// two accumulator stages so tile i's epilogue overlaps tile i+1's MMAs), and a static
-// round-robin tile scheduler (grid = #SMs).  The "dual" modes (local reparameterisation) run
-// two GEMMs with different operands into two TMEM accumulators and join them in the epilogue.
+// Tiles: a CTA pair (cta_group::2) owns a 256 x 256 tile -- each CTA stages its 128 rows of A and half
+// of B, the leader issues the MMAs for both -- or one CTA a 128 x {64,128,256} tile for small problems.
+// Pipelines (mbarriers): smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue; two
+// accumulator stages whenever 2 x accumulators x BLOCK_N <= 512 columns, so tile i's epilogue overlaps
+// tile i+1's MMAs), and the tile scheduler: cluster launch control (one cluster per tile is launched, the
+// resident clusters cancel and absorb the pending ones) or a static round-robin.  The "dual" modes
+// (local reparameterisation) run two GEMMs with different operands into two TMEM accumulators and join
+// them in the epilogue; the multi-sample dW keeps its running sums in spare TMEM columns.
 //
 // Operands may be K-major or MN-major in global memory; MN-major tiles are fetched as
 // {64 x BK} boxes and handed to the MMA through an MN-major shared-memory descriptor, so the
