@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define VBNN_ABI_VERSION 1
+#define VBNN_ABI_VERSION 2
 
 typedef struct vbnn_ctx vbnn_ctx;     /* one per (GPU, host thread)                         */
 typedef struct vbnn_layer vbnn_layer; /* one nn.VBLinear (VBLinear.lua:7) or plain nn.Linear */
@@ -111,6 +111,22 @@ void vbnn_opts_default(vbnn_opts* opts);
  * replaces: require 'cunn' + the implicit cutorch default stream (VBLinear.lua:2, main.lua:1),
  * torch.manualSeed (config.lua:40).  `stream` is a cudaStream_t (NULL = a private stream). */
 int vbnn_ctx_create(int device, void* stream, uint64_t seed, vbnn_ctx** out);
+/* Which stream the context enqueues on.  The reference's other modules (nn.ReLU, nn.LogSoftMax, the
+ * criterion: mlp.lua:19,27,30,32) run on cutorch's LEGACY DEFAULT stream (stream 0), with which a
+ * non-blocking private stream does not synchronise -- a layer-level drop-in must therefore share it:
+ *   VBNN_CTX_STREAM_GIVEN           `stream` as passed (NULL = private non-blocking stream: the net-level
+ *                                   entry points, which own the whole minibatch; = vbnn_ctx_create)
+ *   VBNN_CTX_STREAM_LEGACY_DEFAULT  stream 0 itself (`stream` must be NULL): every call is ordered with
+ *                                   the caller's default-stream work exactly like a cunn module.  CUDA
+ *                                   graphs cannot capture stream 0, so vbnn_mlp_step launches eagerly.
+ *   VBNN_CTX_STREAM_PRIVATE_BLOCKING a private stream created without cudaStreamNonBlocking: it keeps
+ *                                   graph replay and still synchronises implicitly with stream 0. */
+enum vbnn_ctx_stream {
+  VBNN_CTX_STREAM_GIVEN = 0,
+  VBNN_CTX_STREAM_LEGACY_DEFAULT = 1,
+  VBNN_CTX_STREAM_PRIVATE_BLOCKING = 2
+};
+int vbnn_ctx_create_ex(int device, void* stream, int stream_mode, uint64_t seed, vbnn_ctx** out);
 int vbnn_ctx_destroy(vbnn_ctx* ctx);
 int vbnn_ctx_synchronize(vbnn_ctx* ctx);
 /* Per-launch device timing of the tensor-core GEMM: CUDA events on the context's stream around
@@ -171,6 +187,13 @@ int vbnn_layer_calc_lc(vbnn_layer* layer, float* lc_dev, float* sum_host);
 int vbnn_layer_get(vbnn_layer* layer, int which, float* dst_host);
 int vbnn_layer_set(vbnn_layer* layer, int which, const float* src_host);
 int vbnn_layer_device_ptr(vbnn_layer* layer, int which, float** ptr_dev, size_t* count);
+/* Adopt CALLER-OWNED device storage for weight / bias / gradWeight / gradBias (which = VBNN_BUF_WEIGHT,
+ * _BIAS, _GRAD_WEIGHT, _GRAD_BIAS): Torch7's getParameters() (mlp.lua:37) re-flattens these four tensors
+ * of every module into one new storage, so the module must follow them there instead of the other way
+ * round.  The current contents are copied into the caller's buffer, which must stay valid until the next
+ * bind or vbnn_layer_destroy; ptr_dev == NULL hands the buffer back to the library (contents kept).
+ * Layers owned by a vbnn_mlp keep their gradients in the mlp's arena and refuse. */
+int vbnn_layer_bind(vbnn_layer* layer, int which, float* ptr_dev);
 /* optimiser step counters (meanState.t / varState.t / biasState.evalCounter) */
 int vbnn_layer_get_t(vbnn_layer* layer, int* t);
 int vbnn_layer_set_t(vbnn_layer* layer, int t);
@@ -264,6 +287,11 @@ int vbnn_gemm_bf16(vbnn_ctx* ctx, const uint16_t* A_dev, int lda, int a_kmajor,
                    long long strideD);
 int vbnn_philox_normal(vbnn_ctx* ctx, uint64_t seed, uint32_t step, uint32_t stream,
                        uint32_t sample, int rows, int cols, int row0, float* out_dev);
+/* Experiment switches (csrc/knobs.h: "tc_bn", "tc_cg", "lrt_split", "dw_split", "no_graph", ...; the same
+ * names upper-cased with a VBNN_ prefix are read from the environment once per process).  The parity
+ * tests use this to force the CTA-pair 256 x 256 tiles / a GEMM form at oracle-sized problems.
+ * value == INT_MIN restores the default; old_value is nullable.  Unknown name: VBNN_E_INVALID. */
+int vbnn_debug_knob(const char* name, int value, int* old_value);
 
 #ifdef __cplusplus
 }

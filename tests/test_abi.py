@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_defaults_match_config_lua():
     from vbnn_b200 import _lib
     lib = _lib.lib()
-    assert lib.vbnn_abi_version() == 1
+    assert lib.vbnn_abi_version() == 2
     o = _lib.VbnnOpts()
     lib.vbnn_opts_default(o)
     assert abs(o.var_init - 0.001) < 1e-9 and o.mu_init == 0 and o.S == 30       # config.lua:32,43-44

@@ -32,7 +32,7 @@ def cpu(t):
 def test_library_loaded_is_in_tree():
     from vbnn_b200 import _lib
     assert os.path.dirname(_lib.LIB_PATH).endswith("vbnn_b200")
-    assert _lib.lib().vbnn_abi_version() == 1
+    assert _lib.lib().vbnn_abi_version() == 2
 
 
 def test_philox_matches_cpu_restatement(ctx):

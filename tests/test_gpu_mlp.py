@@ -162,13 +162,14 @@ def test_graph_replay_equals_eager(ctx):
     X = torch.from_numpy(rng.randn(32, 40)).float().cuda()
     T = torch.from_numpy(rng.randint(1, 7, 32).astype(np.float32)).cuda()
     outs = []
-    for no_graph in ("1", "0"):
-        os.environ["VBNN_NO_GRAPH"] = no_graph
+    import vbnn_b200
+    for no_graph in (1, 0):
+        vbnn_b200.knob("no_graph", no_graph)
         ctx.set_step(100)
         net, _, _, _ = build_pair(ctx, [40, 48, 36, 6], 32, 2, 30.0, "fp32", "weight", seed=9)
         res = [net.train_step(X, T) for _ in range(4)]
         outs.append((res, cpu(net.model[0].means).copy(), cpu(net.model[1].lvars).copy()))
-    os.environ.pop("VBNN_NO_GRAPH", None)
+    vbnn_b200.knob("no_graph")
     (r0, m0, l0), (r1, m1, l1) = outs
     assert np.allclose(np.array(r0), np.array(r1), rtol=1e-5, atol=1e-6)
     assert rel(m1, m0) < 1e-6 and rel(l1, l0) < 1e-6

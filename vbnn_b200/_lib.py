@@ -46,6 +46,7 @@ _PROTOS = {
     "vbnn_last_error": (C.c_char_p, []),
     "vbnn_opts_default": (None, [C.POINTER(VbnnOpts)]),
     "vbnn_ctx_create": (C.c_int, [C.c_int, _P, C.c_uint64, C.POINTER(_P)]),
+    "vbnn_ctx_create_ex": (C.c_int, [C.c_int, _P, C.c_int, C.c_uint64, C.POINTER(_P)]),
     "vbnn_ctx_destroy": (C.c_int, [_P]),
     "vbnn_ctx_synchronize": (C.c_int, [_P]),
     "vbnn_ctx_profile": (C.c_int, [_P, C.c_int]),
@@ -69,6 +70,7 @@ _PROTOS = {
     "vbnn_layer_get": (C.c_int, [_P, C.c_int, _P]),
     "vbnn_layer_set": (C.c_int, [_P, C.c_int, _P]),
     "vbnn_layer_device_ptr": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_size_t)]),
+    "vbnn_layer_bind": (C.c_int, [_P, C.c_int, _P]),
     "vbnn_layer_get_t": (C.c_int, [_P, C.POINTER(C.c_int)]),
     "vbnn_layer_set_t": (C.c_int, [_P, C.c_int]),
     "vbnn_layer_snr_count": (C.c_int, [_P, C.c_float, _P, C.POINTER(C.c_longlong)]),
@@ -105,7 +107,11 @@ _PROTOS = {
                                  C.c_longlong]),
     "vbnn_philox_normal": (C.c_int, [_P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                      C.c_int, C.c_int, _P]),
+    "vbnn_debug_knob": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_int)]),
 }
+
+STREAM_GIVEN, STREAM_LEGACY_DEFAULT, STREAM_PRIVATE_BLOCKING = 0, 1, 2
+KNOB_DEFAULT = -2 ** 31
 
 _lib = None
 
@@ -139,3 +145,11 @@ def check(code):
     if code != VBNN_OK:
         raise VbnnError(code, lib().vbnn_last_error().decode("utf-8", "replace"))
     return code
+
+
+def knob(name, value=KNOB_DEFAULT):
+    """Set an experiment switch of libvbnn.so (csrc/knobs.h); returns the previous value.
+    knob(name) restores the default / environment value."""
+    old = C.c_int()
+    check(lib().vbnn_debug_knob(name.encode(), int(value), C.byref(old)))
+    return old.value

@@ -11,17 +11,24 @@ from . import _lib as L
 
 
 class Context:
-    def __init__(self, device: int = 0, seed: int = 3):
+    def __init__(self, device: int = 0, seed: int = 3, stream_mode: int = L.STREAM_GIVEN):
+        """stream_mode = L.STREAM_LEGACY_DEFAULT runs the library on stream 0, as a cunn module does
+        (vbnn_ctx_create_ex); the default gives it a torch stream made current for this thread."""
         import torch
         if not torch.cuda.is_available():
             raise L.VbnnError(L.E_CUDA, "no CUDA device: vbnn_b200 has no CPU fallback")
         self.device = device
         torch.cuda.set_device(device)
-        self.stream = torch.cuda.Stream(device=device)
-        torch.cuda.set_stream(self.stream)
         self.handle = C.c_void_p()
-        L.check(L.lib().vbnn_ctx_create(device, C.c_void_p(self.stream.cuda_stream), C.c_uint64(seed),
-                                        C.byref(self.handle)))
+        if stream_mode == L.STREAM_GIVEN:
+            self.stream = torch.cuda.Stream(device=device)
+            torch.cuda.set_stream(self.stream)
+            L.check(L.lib().vbnn_ctx_create_ex(device, C.c_void_p(self.stream.cuda_stream), stream_mode,
+                                               C.c_uint64(seed), C.byref(self.handle)))
+        else:
+            self.stream = torch.cuda.default_stream(device)
+            torch.cuda.set_stream(self.stream)
+            L.check(L.lib().vbnn_ctx_create_ex(device, None, stream_mode, C.c_uint64(seed), C.byref(self.handle)))
         self.seed = seed
         self.rank, self.nranks = 0, 1
 

@@ -23,6 +23,7 @@
 // batch-contracting dW GEMM (D = G^T X) and dX = G W need no transposed copies.
 #include "gemm.h"
 #include "epilogue_tc.cuh"
+#include "knobs.h"
 
 #include <cuda.h>
 #include <stdlib.h>
@@ -783,16 +784,11 @@ int launch_cfg(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
   sh.mt = ceil_div(g.M, BM * CG); sh.nt = ceil_div(g.N, BN); sh.num_kb = ceil_div(g.K, BK);
   sh.zA1 = g.A1.zs != 0; sh.zB1 = g.B1.zs != 0; sh.zA2 = g.A2.zs != 0; sh.zB2 = g.B2.zs != 0;
   {
-    static int gm_env = -1;
-    if (gm_env < 0) { const char* e = getenv("VBNN_TC_GM"); gm_env = e ? atoi(e) : 0; }
-    sh.gm = gm_env > 0 ? gm_env : 8;
+    const Knobs& k = knobs();
+    sh.gm = k.tc_gm > 0 ? k.tc_gm : 8;
     if (sh.gm > sh.mt) sh.gm = sh.mt;
-    static int st_env = -1;
-    if (st_env < 0) { const char* e = getenv("VBNN_TC_STAGED"); st_env = e ? atoi(e) : 1; }
-    sh.staged = st_env && epi_can_stage(MODE, p);
-    static int clc_env = -1;
-    if (clc_env < 0) { const char* e = getenv("VBNN_TC_CLC"); clc_env = e ? atoi(e) : 1; }
-    sh.clc = clc_env;
+    sh.staged = k.tc_staged && epi_can_stage(MODE, p);
+    sh.clc = k.tc_clc;
   }
   CUtensorMap tA1, tB1, tA2, tB2;
   VB_TRY(make_tmap(&tA1, g.A1, g.M, g.K, g.batch, BM));
@@ -841,18 +837,13 @@ int launch_cfg(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
 // 128 x 128 single-CTA tiles.  cost = waves x (tile MACs / relative per-MAC speed).
 template <int MODE>
 TcChoice choose_cfg(const TcGemmArgs& g) {
-  TcChoice c{g_block_n_override, g_cg_override};
-  if (!c.bn) { const char* e = getenv("VBNN_TC_BN"); if (e) c.bn = atoi(e); }      // debugging knobs
-  if (!c.cg) { const char* e = getenv("VBNN_TC_CG"); if (e) c.cg = atoi(e); }
+  const Knobs& k = knobs();
+  TcChoice c{g_block_n_override ? g_block_n_override : k.tc_bn, g_cg_override ? g_cg_override : k.tc_cg};
   if ((c.bn == 128 || c.bn == 256) && (c.cg == 1 || c.cg == 2) && !(c.bn == 128 && c.cg == 2 && !epi_is_dual(MODE))) return c;
   if (epi_z_accumulates(MODE) && g.batch > 1) {
-    static int tacc = -1;
-    if (tacc < 0) { const char* e = getenv("VBNN_TC_TACC"); tacc = e ? atoi(e) : 1; }
     // TMEM-resident accumulators: 128 x 128 tiles (1), or 256 x 128 CTA-pair tiles (2) when M allows
-    if (tacc && !epi_is_dual(MODE)) return TcChoice{128, tacc == 2 && g.M >= 256 ? 2 : 1};
-    static int z64 = -1;
-    if (z64 < 0) { const char* e = getenv("VBNN_TC_DW64"); z64 = e ? atoi(e) : 1; }
-    if (z64) return TcChoice{64, 1};
+    if (k.tc_tacc && !epi_is_dual(MODE)) return TcChoice{128, k.tc_tacc == 2 && g.M >= 256 ? 2 : 1};
+    if (k.tc_dw64) return TcChoice{64, 1};
   }
   const long long zmul = epi_z_accumulates(MODE) ? 1 : g.batch;
   auto cost = [&](int bn, int cg, double speed) {

@@ -6,6 +6,7 @@
 
 #include <vector>
 
+#include "knobs.h"
 #include "state.h"
 
 namespace vbnn {
@@ -100,6 +101,9 @@ int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts
   VB_CHECK(ctx && out && opts, VBNN_E_INVALID, "layer_create: null argument");
   VB_CHECK(I > 0 && O > 0, VBNN_E_INVALID, "layer_create: bad sizes %d x %d", O, I);
   VB_CHECK(kind == VBNN_KIND_VB || kind == VBNN_KIND_LINEAR, VBNN_E_INVALID, "layer_create: bad kind");
+  // the epsilon counter is uint32(o * ceil(I/4) + i/4) (philox.cuh): refuse layers where it would wrap
+  VB_CHECK((unsigned long long)O * (unsigned long long)((I + 3) / 4) <= 0xFFFFFFFFull, VBNN_E_UNSUPPORTED,
+           "layer_create: %d x %d weights exceed the 2^32-quad Philox counter", O, I);
   VB_CUDA(cudaSetDevice(ctx->device));
   vbnn_layer* L = new vbnn_layer();
   L->ctx = ctx; L->I = I; L->O = O; L->kind = kind; L->opts = *opts;
@@ -195,6 +199,16 @@ static void fill_noise(vbnn_layer* L, EpiParams& p, uint32_t kind, const float* 
   p.row0 = 0;
 }
 
+static int bump_layer_t(vbnn_layer* L) {
+  vbnn_ctx* c = L->ctx;
+  VB_CUDA(cudaMemcpyAsync(c->h_scalars, L->t_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  int t = *reinterpret_cast<int*>(c->h_scalars) + 1;
+  VB_CUDA(cudaMemcpyAsync(L->t_dev, &t, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  VB_CUDA(cudaStreamSynchronize(c->stream));
+  return VBNN_OK;
+}
+
 int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
   vbnn_ctx* c = L->ctx;
   cudaStream_t st = c->stream;
@@ -204,6 +218,7 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
     VB_TRY(launch_sgd(L->weight, L->gW, W, L->opts.lr_bias, L->w_bf16, L->I, L->ldI, st));
     VB_TRY(launch_sgd(L->bias, L->gb, L->O, L->opts.lr_bias, nullptr, 1, 1, st));
     c->launches += 2;
+    if (bump_t) VB_TRY(bump_layer_t(L));
     return VBNN_OK;
   }
   VB_TRY(launch_sgd(L->bias, L->gb, L->O, L->opts.lr_bias, nullptr, 1, 1, st));          // VBLinear.lua:125-128
@@ -243,15 +258,9 @@ int layer_update_internal(vbnn_layer* L, vbnn_stats* stats, bool bump_t) {
   }
   c->launches += 2;
   L->prior_valid = true;
-  if (bump_t) {
-    // single counter bump: the layer owns t_dev
-    VB_CUDA(cudaMemcpyAsync(c->h_scalars, L->t_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-    VB_CUDA(cudaStreamSynchronize(st));
-    int t = *reinterpret_cast<int*>(c->h_scalars) + 1;
-    VB_CUDA(cudaMemcpyAsync(L->t_dev, &t, sizeof(int), cudaMemcpyHostToDevice, st));
-    VB_CUDA(cudaStreamSynchronize(st));
-    // the kernel left the new sums in half ((t_old + 1) & 1) == (t & 1): consistent with the bump
-  }
+  // single counter bump: the layer owns t_dev.  The kernel left the new sums in half
+  // ((t_old + 1) & 1) == (t & 1): consistent with the bump
+  if (bump_t) VB_TRY(bump_layer_t(L));
   if (stats) {
     VB_CUDA(cudaMemcpyAsync(c->h_partials, stat_dev, (size_t)grid * kStatSlots * sizeof(double),
                             cudaMemcpyDeviceToHost, st));
@@ -365,7 +374,15 @@ extern "C" void vbnn_opts_default(vbnn_opts* o) {
 
 // ============================================================ context ======================
 extern "C" int vbnn_ctx_create(int device, void* stream, uint64_t seed, vbnn_ctx** out) {
+  return vbnn_ctx_create_ex(device, stream, VBNN_CTX_STREAM_GIVEN, seed, out);
+}
+
+extern "C" int vbnn_ctx_create_ex(int device, void* stream, int stream_mode, uint64_t seed, vbnn_ctx** out) {
   VB_CHECK(out != nullptr, VBNN_E_INVALID, "vbnn_ctx_create: out is null");
+  VB_CHECK(stream_mode >= VBNN_CTX_STREAM_GIVEN && stream_mode <= VBNN_CTX_STREAM_PRIVATE_BLOCKING, VBNN_E_INVALID,
+           "vbnn_ctx_create_ex: bad stream_mode %d", stream_mode);
+  VB_CHECK(stream_mode == VBNN_CTX_STREAM_GIVEN || stream == nullptr, VBNN_E_INVALID,
+           "vbnn_ctx_create_ex: stream must be NULL with stream_mode %d", stream_mode);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -381,8 +398,19 @@ extern "C" int vbnn_ctx_create(int device, void* stream, uint64_t seed, vbnn_ctx
            "libvbnn.so is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
   vbnn_ctx* c = new vbnn_ctx();
   c->device = device; c->seed = seed;
-  if (stream) c->stream = (cudaStream_t)stream;
-  else { VB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  if (stream_mode == VBNN_CTX_STREAM_LEGACY_DEFAULT) {
+    c->stream = cudaStreamLegacy;          // stream 0: ordered with the caller's cutorch-style default-stream work
+    c->capturable = false;
+  } else if (stream_mode == VBNN_CTX_STREAM_PRIVATE_BLOCKING) {
+    VB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault));   // implicit sync with stream 0
+    c->own_stream = true;
+  } else if (stream) {
+    c->stream = (cudaStream_t)stream;
+    c->capturable = c->stream != cudaStreamLegacy && c->stream != cudaStreamPerThread;
+  } else {
+    VB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
   VB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   VB_TRY(dev_zalloc(&c->d_step, 1, c->stream));
   VB_TRY(dev_alloc(&c->d_partials, (size_t)kMaxPartials * (1 + kStatSlots)));
@@ -459,8 +487,14 @@ extern "C" int vbnn_layer_destroy(vbnn_layer* L) {
   if (!L) return VBNN_OK;
   cudaSetDevice(L->ctx->device);
   cudaStreamSynchronize(L->ctx->stream);
-  DEV_FREE(L->means); DEV_FREE(L->lvars); DEV_FREE(L->bias); DEV_FREE(L->weight);
-  if (!L->grads_external) { DEV_FREE(L->gW); DEV_FREE(L->gS); DEV_FREE(L->gb); }
+  DEV_FREE(L->means); DEV_FREE(L->lvars);
+  if (!L->ext_bias) DEV_FREE(L->bias);
+  if (!L->ext_weight) DEV_FREE(L->weight);
+  if (!L->grads_external) {
+    if (!L->ext_gW) DEV_FREE(L->gW);
+    DEV_FREE(L->gS);
+    if (!L->ext_gb) DEV_FREE(L->gb);
+  }
   DEV_FREE(L->m_mu); DEV_FREE(L->v_mu); DEV_FREE(L->m_var); DEV_FREE(L->v_var);
   DEV_FREE(L->eps); DEV_FREE(L->stdv); DEV_FREE(L->mu_sqe); DEV_FREE(L->s2_f32);
   DEV_FREE(L->var_hat_dev); DEV_FREE(L->t_dev); DEV_FREE(L->prior_partials);
@@ -537,6 +571,8 @@ extern "C" int vbnn_layer_forward(vbnn_layer* L, const float* X, int N, float* Y
     mode = EPI_FWD_LRT;
     p.r_out = L->R;
     fill_noise(L, p, kStreamZeta, zeta);
+    VB_CHECK((unsigned long long)N * (unsigned long long)((L->O + 3) / 4) <= 0xFFFFFFFFull, VBNN_E_UNSUPPORTED,
+             "Philox zeta counter would wrap: %d rows x %d outputs", N, L->O);
   }
   if (is_bf16(L)) {
     TcGemmArgs g;
@@ -744,6 +780,47 @@ extern "C" int vbnn_layer_device_ptr(vbnn_layer* L, int which, float** ptr, size
   size_t n;
   VB_TRY(buf_lookup(L, which, ptr, &n));
   if (count) *count = n;
+  return VBNN_OK;
+}
+
+extern "C" int vbnn_layer_bind(vbnn_layer* L, int which, float* ptr) {
+  VB_CHECK(L, VBNN_E_INVALID, "null layer");
+  VB_CHECK(!L->owned_by_mlp, VBNN_E_STATE, "vbnn_layer_bind: the layer belongs to a vbnn_mlp (its gradients live in the mlp's arena)");
+  float** slot = nullptr; bool* ext = nullptr;
+  size_t n = (size_t)L->O * L->I;
+  switch (which) {
+    case VBNN_BUF_WEIGHT: slot = &L->weight; ext = &L->ext_weight; n *= (size_t)L->S_alloc; break;
+    case VBNN_BUF_BIAS: slot = &L->bias; ext = &L->ext_bias; n = L->O; break;
+    case VBNN_BUF_GRAD_WEIGHT: slot = &L->gW; ext = &L->ext_gW; break;
+    case VBNN_BUF_GRAD_BIAS: slot = &L->gb; ext = &L->ext_gb; n = L->O; break;
+    default:
+      set_error("vbnn_layer_bind: buffer %d cannot be caller-owned (weight, bias, gradWeight, gradBias only)", which);
+      return VBNN_E_INVALID;
+  }
+  VB_CHECK(*slot != nullptr, VBNN_E_STATE, "vbnn_layer_bind: buffer %d is not materialised in this mode", which);
+  VB_CHECK(ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) & 3) == 0, VBNN_E_INVALID, "vbnn_layer_bind: unaligned pointer");
+  if (ptr == *slot) return VBNN_OK;
+  cudaStream_t st = L->ctx->stream;
+  float* fresh = ptr;
+  if (!fresh) {                                   // hand the buffer back to the library
+    if (!*ext) return VBNN_OK;
+    VB_TRY(dev_alloc(&fresh, n));
+  }
+  VB_CUDA(cudaMemcpyAsync(fresh, *slot, n * 4, cudaMemcpyDeviceToDevice, st));
+  if (!*ext) {
+    VB_CUDA(cudaStreamSynchronize(st));           // the old buffer may still be read by the copy
+    cudaFree(*slot);
+  }
+  *slot = fresh;
+  *ext = ptr != nullptr;
+  return VBNN_OK;
+}
+
+extern "C" int vbnn_debug_knob(const char* name, int value, int* old_value) {
+  int old = 0;
+  VB_CHECK(knob_get(name, &old) == 0, VBNN_E_INVALID, "vbnn_debug_knob: unknown knob '%s'", name ? name : "(null)");
+  if (old_value) *old_value = old;
+  knob_set(name, value);
   return VBNN_OK;
 }
 

@@ -4,6 +4,7 @@
 // the host except the two scalars main.lua:38-39 accumulates.
 #include <string.h>
 
+#include "knobs.h"
 #include "state.h"
 
 using namespace vbnn;
@@ -32,9 +33,7 @@ inline int nlayers(const vbnn_mlp* m) { return (int)m->layers.size(); }
 // forward is 7 % faster (its Philox-heavy epilogue hides under the MMAs), the split backward-data 3 %
 // slower (its light epilogue gains nothing and the extra fp32 round trip costs energy) -> default 1.
 inline bool lrt_split(const vbnn_mlp* m, int which) {
-  static int env = -1;
-  if (env < 0) { const char* e = getenv("VBNN_LRT_SPLIT"); env = e ? atoi(e) : 1; }
-  return (env & which) != 0 && m->aux != nullptr;
+  return (knobs().lrt_split & which) != 0 && m->aux != nullptr;
 }
 
 // ---- stage the caller's minibatch into operand form (outside the graph: pointers vary) ----
@@ -111,6 +110,9 @@ int forward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, bool map_mod
     p.ps = layer_stream(L, kStreamZeta, sample0);
     p.step_ptr = m->ctx->d_step;
     p.row0 = m->ctx->rank * N;
+    // the zeta counter is uint32(global row * ceil(O/4) + col/4): refuse shapes where it would wrap
+    VB_CHECK((unsigned long long)m->ctx->nranks * (unsigned long long)N * (unsigned long long)((L->O + 3) / 4) <= 0xFFFFFFFFull,
+             VBNN_E_UNSUPPORTED, "Philox zeta counter would wrap: %d ranks x %d rows x %d outputs", m->ctx->nranks, N, L->O);
   }
   if (m->bf16) {
     TcGemmArgs g;
@@ -252,9 +254,8 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
     // Dual dW (one launch, two accumulators, single-buffered TMEM) or two single-accumulator GEMMs
     // (double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1).  On one GPU they tie; in
     // peer mode the epilogue's stores cross NVLink and the split form hides them (8 GPUs: 6.14 -> 5.97 ms).
-    static int split_env = -2;
-    if (split_env == -2) { const char* e = getenv("VBNN_DW_SPLIT"); split_env = e ? atoi(e) : -1; }
-    const bool split = split_env >= 0 ? split_env != 0 : scatter;
+    const int split_knob = knobs().dw_split;
+    const bool split = split_knob >= 0 ? split_knob != 0 : scatter;
     if (m->bf16 && lrt && split) {
       // The two LRT parameter gradients are independent (g_mu = G^T X, g_s = H^T X^2): as two
       // single-accumulator GEMMs each tile needs half the TMEM, so the accumulator is double-buffered
@@ -384,9 +385,7 @@ int step_body(vbnn_mlp* m, int N) {
   VB_TRY(sample_all(m, 0, m->Z));                                                              // :33
   VB_TRY(prof_mark(m->ctx, 2));
   const bool dp = m->ctx->nranks > 1;
-  static int ov_env = -1;
-  if (ov_env < 0) { const char* e = getenv("VBNN_DP_OVERLAP"); ov_env = e ? atoi(e) : 1; }
-  const bool overlap = dp && ov_env && m->ctx->comm_stream != nullptr;
+  const bool overlap = dp && knobs().dp_overlap && m->ctx->comm_stream != nullptr;
   VB_TRY(run_samples(m, N, m->Z, 0, /*accumulate=*/0, true, overlap));                         // :34
   if (dp && !overlap) VB_TRY(comm_allreduce_internal(m->ctx, m->grad_arena, m->grad_count, st));
   VB_TRY(update_all(m, overlap));                                                              // :40
@@ -401,7 +400,7 @@ int step_body(vbnn_mlp* m, int N) {
 int step_enqueue(vbnn_mlp* m, int N) {
   vbnn_ctx* c = m->ctx;
   cudaStream_t st = c->stream;
-  const bool graphable = m->use_graph && c->nranks == 1 && !c->profiling;
+  const bool graphable = m->use_graph && c->capturable && c->nranks == 1 && !c->profiling;
   if (!graphable || m->eager_steps < 1) {
     m->eager_steps++;
     return step_body(m, N);
@@ -523,8 +522,7 @@ extern "C" int vbnn_mlp_create(vbnn_ctx* ctx, const int* sizes, int n_sizes, int
         cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) { r = VBNN_E_CUDA; break; }
     m->ev_bwd.push_back(a); m->ev_red.push_back(b);
   }
-  const char* env = getenv("VBNN_NO_GRAPH");
-  if (env && env[0] == '1') m->use_graph = false;
+  if (knobs().no_graph) m->use_graph = false;
   if (r != VBNN_OK) { vbnn_mlp_destroy(m); return r; }
   *out = m;
   return VBNN_OK;

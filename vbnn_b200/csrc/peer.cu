@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <string.h>
 
+#include "knobs.h"
 #include "state.h"
 
 namespace vbnn {
@@ -272,9 +273,7 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     u.lr_mu = L->opts.lr_mu; u.lr_var = L->opts.lr_var;
     u.beta1 = L->opts.adam_beta1; u.beta2 = L->opts.adam_beta2; u.eps = L->opts.adam_eps;
     u.lrt = layer_lrt(L);
-    static int l0_env = -1;
-    if (l0_env < 0) { const char* e = getenv("VBNN_PEER_L0_PUSH"); l0_env = (e && !strcmp(e, "ce")) ? 0 : 1; }
-    const bool fused_push = j == 0 && l0_env && pl.rows > 0;
+    const bool fused_push = j == 0 && knobs().peer_l0_push && pl.rows > 0;
     if (fused_push) {
       // layer 0: its update is the tail of the minibatch -- the SMs and NVLink are otherwise idle, so the
       // kernel stores the refreshed operands to every rank itself instead of 2 x (G-1) serial copies

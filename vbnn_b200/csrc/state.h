@@ -10,6 +10,7 @@ struct vbnn_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  bool capturable = true;            // false on the legacy default stream (CUDA graphs cannot capture stream 0)
   cudaStream_t copy_stream = nullptr;
   uint64_t seed = 0;
   uint32_t* d_step = nullptr;        // Philox "minibatch" counter, lives on the device (graph-safe)
@@ -42,6 +43,7 @@ struct vbnn_layer {
   int S_alloc = 1;                   // weight samples held at once
   bool owned_by_mlp = false;
   bool grads_external = false;       // gW/gS/gb live in the mlp's allreduce arena
+  bool ext_weight = false, ext_bias = false, ext_gW = false, ext_gb = false;   // caller-owned (vbnn_layer_bind)
   // fp32 master state, dense [O x I] / [O]
   float *means = nullptr, *lvars = nullptr, *bias = nullptr, *weight = nullptr;
   float *gW = nullptr, *gS = nullptr, *gb = nullptr;

@@ -105,6 +105,19 @@ class MLP:
         return v.value
 
     def update(self, opt=None):                                         # mlp.lua:117-142
+        opt = opt or self.opt
+        from . import logger
+        if opt.get("log") and logger.Log is not None and self.ctx.nranks == 1:
+            # with logging on the reference syncs >= 13 scalars per layer anyway (VBLinear.lua:150-163): go
+            # layer by layer so every VBLinear reports its 14 diagnostics -- output-layer SGD first
+            # (mlp.lua:120-123), then the VB layers in index order (:138-140); all layers log to the same
+            # ids, interleaved, exactly as the reference does
+            if self.model[-1].kind == L.KIND_LINEAR:
+                L.check(L.lib().vbnn_layer_update(self.model[-1].handle, None))
+            for k in self.vb_indices:
+                self.model[k].update(opt)
+            self.ctx.set_step(self.ctx.get_step() + 1)
+            return
         L.check(L.lib().vbnn_mlp_update(self.handle))
 
     # ---- fused minibatch: main.lua:28-40 in one call ----

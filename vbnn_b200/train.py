@@ -27,6 +27,9 @@ def create_minibatch(dataset, index, batchSize, n):
 def train(net, dataset, opt, fused=True, shuffle_seed=None):
     """main:train (main.lua:13-53).  Returns (accuracy/B, error/B)."""
     import torch
+    from . import logger
+    if opt.get("log") and logger.Log is not None:
+        fused = False       # per-minibatch diagnostics (VBLinear.lua:150-163) come from the piecewise update
     B = opt["trainSize"] / opt["batchSize"]                             # main.lua:17
     starts = torch.arange(0, opt["trainSize"], opt["batchSize"])        # main.lua:18
     g = torch.Generator().manual_seed(shuffle_seed) if shuffle_seed is not None else None
@@ -65,3 +68,24 @@ def test(net, dataset, opt):
         accuracy += acc
         error += err
     return accuracy / B, error / B
+
+
+def epoch(net, trainSet, testSet, opt, fused=True, shuffle_seed=None):
+    """One pass of the `while true` loop of main:run (main.lua:164-182): train, test, the five epoch metrics
+    into the logger's per-id files (`devacc`, `trainacc`, `deverr`, `trainerr`, `lc`), flush, checkpoint."""
+    from . import checkpoint, logger
+    trainAccuracy, trainError = train(net, trainSet, opt, fused=fused, shuffle_seed=shuffle_seed)
+    testAccuracy, testError = test(net, testSet, opt)
+    lc = None
+    if opt.get("log") and logger.Log is not None:
+        Log = logger.Log
+        Log.add("devacc", testAccuracy)                                 # main.lua:170-173
+        Log.add("trainacc", trainAccuracy)
+        Log.add("deverr", testError)
+        Log.add("trainerr", trainError)
+        if opt.get("type", "vb") == "vb":
+            lc = net.calc_lc(opt)                                       # main.lua:175
+            Log.add("lc", lc)
+        Log.flush()                                                     # main.lua:179
+    checkpoint.save_net(net, opt["network_name"], "model")              # main.lua:181
+    return trainAccuracy, trainError, testAccuracy, testError, lc

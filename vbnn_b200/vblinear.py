@@ -211,6 +211,10 @@ class VBLinear:
             L.check(L.lib().vbnn_layer_update(self.handle, C.byref(st)))
             self.stats = {name: getattr(st, f) for name, (f, _) in zip(L.STAT_NAMES, L.VbnnStats._fields_)}
             self.var_hat = st.var_hat
+            from . import logger
+            if logger.Log is not None:                                  # VBLinear.lua:150-163
+                for name in L.STAT_NAMES:
+                    logger.Log.add(name, self.stats[name])
             return self.stats
         L.check(L.lib().vbnn_layer_update(self.handle, None))
         return None
@@ -219,6 +223,14 @@ class VBLinear:
         c = C.c_longlong()
         L.check(L.lib().vbnn_layer_snr_count(self.handle, C.c_float(thresh), None, C.byref(c)))
         return c.value
+
+    def snr_prune_mask(self, thresh=0.005):
+        """(mask [O x I] uint8 on the device, count): mainviz.lua:20-22 `torch.lt(|mu| / sigma, thresh)`."""
+        import torch
+        mask = torch.empty(self.outputSize, self.inputSize, dtype=torch.uint8, device=f"cuda:{self.ctx.device}")
+        c = C.c_longlong()
+        L.check(L.lib().vbnn_layer_snr_count(self.handle, C.c_float(thresh), C.c_void_p(mask.data_ptr()), C.byref(c)))
+        return mask, c.value
 
     def draw_noise(self, step, sample_idx, rows=0, row0=0):
         """The epsilon [O x I] (or zeta [rows x O] under local reparameterisation) the fused
