@@ -190,8 +190,9 @@ int vbnn_layer_device_ptr(vbnn_layer* layer, int which, float** ptr_dev, size_t*
 /* Adopt CALLER-OWNED device storage for weight / bias / gradWeight / gradBias (which = VBNN_BUF_WEIGHT,
  * _BIAS, _GRAD_WEIGHT, _GRAD_BIAS): Torch7's getParameters() (mlp.lua:37) re-flattens these four tensors
  * of every module into one new storage, so the module must follow them there instead of the other way
- * round.  The current contents are copied into the caller's buffer, which must stay valid until the next
- * bind or vbnn_layer_destroy; ptr_dev == NULL hands the buffer back to the library (contents kept).
+ * round.  The caller's buffer is adopted AS IS (Torch copies the old values into the flat storage itself,
+ * and mlp.lua:48-54 then rewrites weight / bias there: the tensor is the parameter) and must stay valid until
+ * the next bind or vbnn_layer_destroy; ptr_dev == NULL hands the buffer back to the library (contents kept).
  * Layers owned by a vbnn_mlp keep their gradients in the mlp's arena and refuse. */
 int vbnn_layer_bind(vbnn_layer* layer, int which, float* ptr_dev);
 /* optimiser step counters (meanState.t / varState.t / biasState.evalCounter) */
@@ -240,6 +241,16 @@ int vbnn_mlp_step_host(vbnn_mlp* mlp, const float* X_host, const float* targets_
  * collect returns the {error, accuracy} of the oldest submitted minibatch. */
 int vbnn_mlp_submit_host(vbnn_mlp* mlp, const float* X_host, const float* targets_host, int N);
 int vbnn_mlp_collect(vbnn_mlp* mlp, float* err_host, float* acc_host);
+/* The same pipeline fed with the dataset's NATIVE bytes: MNIST pixels are uint8 before data.lua:25,30
+ * (u.normalize, utils.lua:29-35) turns them into (x - mean) / std floats on the host.  Here the bytes cross
+ * PCIe (4x fewer than fp32) and the normalisation is fused into the operand-staging kernel on the device:
+ * x = (float(byte) - mean) * inv_std, then exactly the path of vbnn_mlp_submit_host. */
+int vbnn_mlp_submit_host_u8(vbnn_mlp* mlp, const uint8_t* X_host, const float* targets_host, int N,
+                            float mean, float inv_std);
+/* Make the context's stream wait for everything a minibatch enqueued on the library's auxiliary streams (the
+ * peer-mode side stream: last shard update + operand push; the NCCL stream), so that an event recorded on the
+ * context's stream afterwards covers the WHOLE minibatch.  Asynchronous; a no-op on one GPU. */
+int vbnn_mlp_join_streams(vbnn_mlp* mlp);
 
 /* net:test(input, target)  mlp.lua:86-107: n_samples == 0 -> clamp_to_map (quicktest),
  * else mean over n_samples sampled forward passes (no wasted backward). */

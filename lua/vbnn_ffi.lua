@@ -18,7 +18,7 @@ typedef struct vbnn_stats {
 } vbnn_stats;
 const char* vbnn_last_error(void);
 void vbnn_opts_default(vbnn_opts*);
-int vbnn_ctx_create(int device, void* stream, uint64_t seed, vbnn_ctx** out);
+int vbnn_ctx_create_ex(int device, void* stream, int stream_mode, uint64_t seed, vbnn_ctx** out);
 int vbnn_ctx_destroy(vbnn_ctx*);
 int vbnn_layer_create(vbnn_ctx*, int inputSize, int outputSize, int kind, const vbnn_opts*, vbnn_layer** out);
 int vbnn_layer_destroy(vbnn_layer*);
@@ -33,6 +33,7 @@ int vbnn_layer_grads(vbnn_layer*, float* mleg, float* mlcg, float* vleg, float* 
 int vbnn_layer_update(vbnn_layer*, vbnn_stats*);
 int vbnn_layer_calc_lc(vbnn_layer*, float* lc_dev, float* sum_host);
 int vbnn_layer_device_ptr(vbnn_layer*, int which, float** ptr_dev, size_t* count);
+int vbnn_layer_bind(vbnn_layer*, int which, float* ptr_dev);
 /* net level (lua/mlp.lua): the mlp.lua object and the main.lua:19-51 closure */
 typedef struct vbnn_mlp vbnn_mlp;
 int vbnn_mlp_create(vbnn_ctx*, const int* sizes, int n_sizes, int vb_output, int max_batch, const vbnn_opts*, vbnn_mlp** out);
@@ -64,13 +65,35 @@ function M.check(rc)
    if rc ~= 0 then error('libvbnn: ' .. ffi.string(C.vbnn_last_error()), 2) end
 end
 
+-- stream modes: the enum of include/vbnn.h next to vbnn_ctx_create_ex
+M.STREAM_GIVEN, M.STREAM_LEGACY_DEFAULT = 0, 1
+
+-- cutorch's CURRENT stream, the one nn.ReLU / nn.LogSoftMax / the criterion (mlp.lua:19,27,30,32) enqueue on:
+-- THCState_getCurrentStream(cutorch.getState()) from libTHC.  cutorch's default stream -- and the only
+-- stream of the early-2015 cutorch the reference was written against -- is CUDA's legacy default stream
+-- (stream 0, a NULL cudaStream_t): the library is then told so explicitly, because a NULL `stream` alone
+-- would mean "give me a private stream", which does not synchronise with stream 0.
+local function cutorch_stream()
+   local ok, s = pcall(function()
+      ffi.cdef[[ typedef struct THCState THCState; void* THCState_getCurrentStream(THCState* state); ]]
+      local THC = ffi.load('THC')
+      return THC.THCState_getCurrentStream(ffi.cast('THCState*', cutorch.getState()))
+   end)
+   if ok and s ~= nil then return s end
+   return nil                                   -- stream 0 (or a cutorch without streams)
+end
+
 -- one context per process, on cutorch's current device and stream
 function M.context(seed)
    if not M.ctx then
       local out = ffi.new('vbnn_ctx*[1]')
       local dev = cutorch.getDevice() - 1
-      local stream = cutorch.getStream and cutorch._state and nil or nil  -- NULL: private stream
-      M.check(C.vbnn_ctx_create(dev, stream, seed or 3, out))
+      local stream = cutorch_stream()
+      if stream ~= nil then
+         M.check(C.vbnn_ctx_create_ex(dev, stream, M.STREAM_GIVEN, seed or 3, out))
+      else
+         M.check(C.vbnn_ctx_create_ex(dev, nil, M.STREAM_LEGACY_DEFAULT, seed or 3, out))
+      end
       M.ctx = ffi.gc(out[0], C.vbnn_ctx_destroy)
    end
    return M.ctx
@@ -88,10 +111,11 @@ function M.opts(opt)
    return o
 end
 
--- raw device pointer of a CudaTensor (contiguous, float)
+-- raw device pointer of a contiguous CudaTensor: cutorch's FFI accessor tensor:data() returns a float* to
+-- the first element (storage data + storageOffset), on the device
 function M.ptr(t)
    assert(t:isContiguous(), 'libvbnn needs contiguous tensors')
-   return ffi.cast('float*', torch.pointer(t:storage():data()) + 0) + (t:storageOffset() - 1)
+   return ffi.cast('float*', t:data())
 end
 
 return M

@@ -494,6 +494,31 @@ def train_minibatch(net: MLPOracle, inputs, targets, opt=None, eps=None, zeta=No
     return serr / opt["S"], sacc / opt["S"]
 
 
+def train_epoch(net: MLPOracle, dataset: dict, opt: dict, order: Sequence[int], eps_fn=None, zeta_fn=None):
+    """main:train (main.lua:13-53): B = trainSize / batchSize minibatches visited in the (shuffled,
+    utils.lua:90-94) order of start indices `order`; minibatch assembly as data.lua:9-20 (rows
+    [t, t + batchSize) of the dataset).  eps_fn(i) / zeta_fn(i) return the injected noise of the i-th
+    visited minibatch.  Returns (accuracy / B, error / B) as main.lua:52."""
+    B = opt["trainSize"] / opt["batchSize"]                               # main.lua:17
+    accuracy = error = 0.0
+    for i, t in enumerate(order):                                         # main.lua:18-19
+        hi = min(t + opt["batchSize"], opt["trainSize"])
+        inputs, targets = dataset["inputs"][t:hi], dataset["targets"][t:hi]   # main.lua:21
+        err, acc = train_minibatch(net, inputs, targets, opt,
+                                   eps=None if eps_fn is None else eps_fn(i),
+                                   zeta=None if zeta_fn is None else zeta_fn(i))
+        accuracy += acc                                                   # main.lua:38
+        error += err                                                      # main.lua:39
+    return accuracy / B, error / B
+
+
+def snr_prune_mask(means: torch.Tensor, lvars: torch.Tensor, thresh: float = 0.005):
+    """mainviz.lua:20-22: pruned = torch.lt(torch.abs(torch.cdiv(means, torch.sqrt(vars))), 0.005), with
+    vars = exp(lvars).  Returns (mask, count)."""
+    pruned = torch.lt(torch.abs(means / torch.sqrt(torch.exp(lvars))), thresh)
+    return pruned, int(pruned.sum())
+
+
 # ----------------------------------------------------------------------------
 # Philox4x32-10 + Box-Muller, the counter layout of libvbnn.so (csrc/philox.cuh).
 # Lets tests regenerate on the CPU exactly the epsilon the fused GPU kernels draw.

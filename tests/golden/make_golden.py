@@ -102,10 +102,28 @@ def mlp_case(seed=21, steps=2):
     return out
 
 
+def write_replay_bin():
+    """mlp_weight.npz as a flat little-endian file the C++ replay host (tools/replay.cu) can read without a zip /
+    npy parser: "VBRP", u32 count, then per array: u32 name_len, name, u32 ndim, u32 dims[ndim], f32 data."""
+    import struct
+    g = np.load(os.path.join(HERE, "mlp_weight.npz"))
+    with open(os.path.join(HERE, "mlp_weight.replay.bin"), "wb") as f:
+        f.write(b"VBRP" + struct.pack("<I", len(g.files)))
+        for k in g.files:
+            a = np.atleast_1d(np.asarray(g[k], dtype=np.float64)).astype("<f4")
+            f.write(struct.pack("<I", len(k)) + k.encode() + struct.pack("<I", a.ndim))
+            f.write(struct.pack(f"<{a.ndim}I", *a.shape))
+            f.write(a.tobytes())
+
+
 if __name__ == "__main__":
+    if "--replay-only" in sys.argv:
+        write_replay_bin()
+        sys.exit(0)
     np.savez_compressed(os.path.join(HERE, "vblinear_weight.npz"), **layer_case("weight"))
     np.savez_compressed(os.path.join(HERE, "vblinear_local.npz"), **layer_case("local"))
     np.savez_compressed(os.path.join(HERE, "mlp_weight.npz"), **mlp_case())
+    write_replay_bin()
     for f in sorted(os.listdir(HERE)):
-        if f.endswith(".npz"):
+        if f.endswith(".npz") or f.endswith(".bin"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

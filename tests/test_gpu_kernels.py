@@ -230,3 +230,57 @@ def test_error_behaviour(ctx):
     y = lyr2.updateOutput(torch.ones(1, 10, device="cuda"))
     assert y.shape == (1, 3) and bool(torch.isfinite(y).all())
     assert lyr2.snr_prune_count(1e9) == 30
+
+
+def test_layer_on_legacy_default_stream_with_bound_storage():
+    """The layer-level drop-in as the Lua shim uses it: a context on the LEGACY DEFAULT stream
+    (vbnn_ctx_create_ex, VBNN_CTX_STREAM_LEGACY_DEFAULT -- where cutorch's nn.ReLU / criterion run) and
+    weight / bias / gradWeight / gradBias adopted from caller-owned flat storage (vbnn_layer_bind, the
+    getParameters() re-flattening of mlp.lua:37), interleaved with default-stream torch work and no explicit
+    synchronisation; against the committed fp64 fixture."""
+    import vbnn_b200
+    from vbnn_b200 import _lib as L
+    g = np.load(os.path.join(GOLD, "vblinear_weight.npz"))
+    I, Ol, S = int(g["I"]), int(g["O"]), int(g["S"])
+    old_stream = torch.cuda.current_stream()
+    lctx = vbnn_b200.Context(0, seed=5, stream_mode=L.STREAM_LEGACY_DEFAULT)
+    try:
+        opt = vbnn_b200.default_opt(B=float(g["B"]), S=S, mu_init=1, var_init=0.01, log=False)
+        lyr = vbnn_b200.VBLinear(I, Ol, opt, lctx)
+        lyr.set(L.BUF_MEANS, g["means0"]); lyr.set(L.BUF_LVARS, g["lvars0"])
+        flat_p = torch.zeros(Ol * I + Ol, device="cuda")                 # getParameters(): {weight, bias}
+        flat_p[Ol * I:] = torch.from_numpy(g["bias0"]).float().cuda()    # the tensor is the parameter: adopted as is
+        flat_g = torch.full((Ol * I + Ol,), 7.0, device="cuda")          # garbage until gradParameters:zero()
+        for which, t in ((L.BUF_WEIGHT, flat_p[:Ol * I]), (L.BUF_BIAS, flat_p[Ol * I:]),
+                         (L.BUF_GRAD_WEIGHT, flat_g[:Ol * I]), (L.BUF_GRAD_BIAS, flat_g[Ol * I:])):
+            L.check(L.lib().vbnn_layer_bind(lyr.handle, which, C.c_void_p(t.data_ptr())))
+        assert lyr.gradWeight.data_ptr() == flat_g.data_ptr()            # the module's view follows the flat storage
+        assert rel(cpu(lyr.bias), g["bias0"]) < 1e-7                     # the caller's values are the layer's now
+        lyr.compute_prior()
+        with torch.cuda.stream(torch.cuda.default_stream()):
+            flat_g.zero_()                                               # gradParameters:zero() (mlp.lua:63), stream 0
+            lyr.resetAcc()
+            X = torch.from_numpy(g["X"]).float().cuda()
+            for s in range(S):
+                G = torch.from_numpy(g[f"G{s}"]).float().cuda()
+                lyr.sample(eps=torch.from_numpy(g[f"noise{s}"]).float().cuda(), sample_idx=s)
+                X2 = (X * 3.0) / 3.0 + 0.0                               # default-stream producer of the input
+                Y = lyr.updateOutput(X2)
+                Yc = Y * 1.0                                             # default-stream consumer of the output
+                dX = lyr.updateGradInput(X2, G * 1.0)
+                lyr.accGradParameters(X2, G, 1.0)
+                assert rel(cpu(Yc), g[f"Y{s}"]) < 1e-5 and rel(cpu(dX), g[f"dX{s}"]) < 2e-5
+            assert rel(cpu(flat_g[:Ol * I]), g["gradWeight"].ravel()) < 1e-5     # accumulated IN the flat storage
+            assert rel(cpu(flat_g[Ol * I:]), g["gradBias"]) < 1e-5
+            assert rel(cpu(flat_p[:Ol * I].view(Ol, I)), cpu(lyr._view(L.BUF_WEIGHT))) == 0.0
+            lyr.update(opt)
+            assert rel(cpu(flat_p[Ol * I:]), g["bias1"]) < 1e-5          # SGD on the bound bias (VBLinear.lua:125-128)
+            assert rel(cpu(lyr.means), g["means1"]) < 1e-5
+        for which in (L.BUF_WEIGHT, L.BUF_BIAS, L.BUF_GRAD_WEIGHT, L.BUF_GRAD_BIAS):
+            L.check(L.lib().vbnn_layer_bind(lyr.handle, which, None))    # hand back before the tensors die
+        assert lyr.gradWeight.data_ptr() != flat_g.data_ptr()
+        assert rel(cpu(lyr.bias), g["bias1"]) < 1e-5
+        del lyr
+    finally:
+        lctx.close()
+        torch.cuda.set_stream(old_stream)

@@ -459,3 +459,253 @@ def test_c3_exact_size_properties(ctx):
         assert relt(a, b) < 0.15
     for a, b in zip(res["bf16"][3], res["fp32"][3]):
         assert relt(a, b) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------
+# The CTA-pair (cta_group::2, 256 x 256) tiles are what bench.py times on C3; at oracle-sized problems the
+# cost model picks 128 x 128 single-CTA tiles, so these tests FORCE the pair tiles (vbnn_debug_knob) at a
+# size with >= 2 pair tiles per dimension and ragged edges in every dimension, and compare every GEMM form
+# (dual / split forward, dual / split backward-data, dual / split dW, weight-mode fwd / dx / multi-sample dW)
+# with the bf16-rounding oracle at the tight tolerance.
+@pytest.mark.parametrize("reparam,S,lrt_split,dw_split", [("local", 1, 1, 0),    # bench default: split fwd, dual dx, dual dW
+                                                          ("local", 1, 0, 1),    # dual fwd, split dW (the peer-mode form)
+                                                          ("local", 2, 3, 0),    # split fwd + split dx, 2 samples
+                                                          ("weight", 1, 1, 0),   # EPI_FWD / EPI_DX / EPI_DW pair tiles
+                                                          ("weight", 3, 1, 0)])  # multi-sample dW, global accumulate
+def test_pair_tile_epilogues_vs_oracle(ctx, reparam, S, lrt_split, dw_split):
+    import vbnn_b200
+    sizes, N = [600, 552, 530, 10], 540
+    old = [vbnn_b200.knob("tc_bn", 256), vbnn_b200.knob("tc_cg", 2), vbnn_b200.knob("lrt_split", lrt_split),
+           vbnn_b200.knob("dw_split", dw_split)]
+    try:
+        net, ref, gopt, oopt = build_pair(ctx, sizes, N, S, 30.0, "bf16", reparam, seed=7, strict=False,
+                                          operand_round=O.round_bf16)
+        rng = np.random.RandomState(17)
+        nvb = len(ref.vb_all)
+        for it in range(2):                       # second minibatch: graph replay + Adam state carried over
+            Xn = rng.randn(N, sizes[0]); Tn = rng.randint(1, sizes[-1] + 1, N).astype(np.float64)
+            step = ctx.get_step()
+            noise = [[torch.from_numpy(cpu(net.model[k].draw_noise(step, s, rows=N)).astype(np.float64))
+                      for k in range(nvb)] for s in range(S)]
+            err, acc = net.train_step(torch.from_numpy(Xn).float().cuda(), torch.from_numpy(Tn).float().cuda())
+            kw = dict(zeta=noise) if reparam == "local" else dict(eps=noise)
+            rerr, racc, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), **kw)
+            assert abs(err - rerr) < 2e-3 * abs(rerr), (it, err, rerr)
+            for k, ol in enumerate(ref.vb_all):
+                gl = net.model[k]
+                gw, gs, gb = accs[k]
+                # per 64-row band as well as whole-tensor: a wrong 32-column chunk or a row offset in ONE CTA
+                # of the pair would be diluted in the Frobenius norm of the whole matrix, not in its band
+                G, Gr = cpu(gl.gradWeight), gw.numpy()
+                S_, Sr = cpu(gl.gradSum), gs.numpy()
+                assert rel(G, Gr) < 5e-3 and rel(S_, Sr) < 1e-2, (it, k)
+                for r0 in range(0, G.shape[0], 64):
+                    assert rel(G[r0:r0 + 64], Gr[r0:r0 + 64]) < 1e-2, (it, k, "gW rows", r0)
+                    assert rel(S_[r0:r0 + 64], Sr[r0:r0 + 64]) < 2e-2, (it, k, "gS rows", r0)
+                for c0 in range(0, G.shape[1], 64):
+                    assert rel(G[:, c0:c0 + 64], Gr[:, c0:c0 + 64]) < 1e-2, (it, k, "gW cols", c0)
+                    assert rel(S_[:, c0:c0 + 64], Sr[:, c0:c0 + 64]) < 2e-2, (it, k, "gS cols", c0)
+                assert rel(cpu(gl.gradBias), gb.numpy()) < 5e-3, (it, k, "gb")
+                assert rel(cpu(gl.means), ol.means.numpy()) < 5e-3, (it, k, "means")
+                assert rel(cpu(gl.lvars), ol.lvars.numpy()) < 5e-3, (it, k, "lvars")
+            assert rel(cpu(net.model[-1].weight), ref.out.weight.numpy()) < 5e-3
+            assert rel(cpu(net.model[-1].gradWeight), ref.out.gradWeight.numpy()) < 5e-3
+    finally:
+        for name, v in zip(("tc_bn", "tc_cg", "lrt_split", "dw_split"), old):
+            vbnn_b200.knob(name, v)
+
+
+@pytest.mark.parametrize("M,N,K", [(540, 600, 552), (530, 552, 540)])
+def test_pair_tile_layer_outputs_vs_torch(ctx, M, N, K):
+    """The same forced pair tiles on the raw GEMM (EPI_STORE -> the `aux` product of the split forms): every
+    element against fp64 on bf16-rounded operands (fp32 accumulate: <= 1e-5)."""
+    import vbnn_b200
+    from vbnn_b200 import _lib as L
+    import ctypes as C
+    old = [vbnn_b200.knob("tc_bn", 256), vbnn_b200.knob("tc_cg", 2)]
+    try:
+        g = torch.Generator().manual_seed(M + N)
+        r8 = lambda v: (v + 7) // 8 * 8
+        for ak, bk in ((1, 1), (1, 0), (0, 0)):                      # fwd, dx, dw operand majors
+            A = torch.randn(M, K, generator=g).bfloat16(); B = torch.randn(N, K, generator=g).bfloat16()
+            ref = (A.double() @ B.double().t()).numpy()
+            if ak:
+                lda = r8(K); Ad = torch.zeros(M, lda, dtype=torch.bfloat16); Ad[:, :K] = A
+            else:
+                lda = r8(M); Ad = torch.zeros(K, lda, dtype=torch.bfloat16); Ad[:, :M] = A.t()
+            if bk:
+                ldb = r8(K); Bd = torch.zeros(N, ldb, dtype=torch.bfloat16); Bd[:, :K] = B
+            else:
+                ldb = r8(N); Bd = torch.zeros(K, ldb, dtype=torch.bfloat16); Bd[:, :N] = B.t()
+            Ad, Bd = Ad.cuda(), Bd.cuda()
+            ldd = r8(N)
+            D = torch.full((M, ldd), float("nan"), device="cuda")
+            L.check(L.lib().vbnn_gemm_bf16(ctx.handle, C.c_void_p(Ad.data_ptr()), lda, ak, C.c_void_p(Bd.data_ptr()), ldb, bk,
+                                           C.c_void_p(D.data_ptr()), ldd, M, N, K, 1, 0, 0, 0))
+            ctx.synchronize()
+            got = cpu(D)[:, :N]
+            assert np.isfinite(got).all()
+            assert np.abs(got - ref).max() < 1e-4 * max(1.0, np.abs(ref).max()), (ak, bk)
+    finally:
+        vbnn_b200.knob("tc_bn", old[0]); vbnn_b200.knob("tc_cg", old[1])
+
+
+def test_snr_mask_vs_oracle(ctx):
+    """the signal-to-noise pruning mask of mainviz.lua:20-24 on random parameters whose
+    |mu|/sigma straddles the threshold, element for element against the oracle restatement."""
+    import vbnn_b200
+    from vbnn_b200 import _lib as L
+    opt = vbnn_b200.default_opt(S=1, B=50.0, mu_init=1, var_init=0.01, strict_reference=False, log=False)
+    lyr = vbnn_b200.VBLinear(203, 77, opt, ctx)
+    rng = np.random.RandomState(4)
+    lv = rng.uniform(math.log(1e-4), math.log(1e-1), (77, 203)).astype(np.float32)
+    snr = np.abs(rng.standard_cauchy((77, 203))) * 0.005              # about half below the 0.005 threshold
+    sign = rng.choice([-1.0, 1.0], (77, 203))
+    mu = (sign * snr * np.exp(0.5 * lv.astype(np.float64))).astype(np.float32)
+    lyr.set(L.BUF_MEANS, mu); lyr.set(L.BUF_LVARS, lv)
+    for thresh in (0.005, 0.001, 0.05):
+        mask, count = lyr.snr_prune_mask(thresh)
+        rmask, rcount = O.snr_prune_mask(torch.from_numpy(mu).double(), torch.from_numpy(lv).double(), thresh)
+        got = mask.cpu().numpy().astype(bool)
+        want = rmask.numpy()
+        # fp32 exp / divide on the GPU vs fp64: only elements within 1e-5 (relative) of the threshold may differ
+        ratio = np.abs(mu.astype(np.float64)) / np.exp(0.5 * lv.astype(np.float64))
+        near = np.abs(ratio - thresh) < 1e-5 * thresh
+        assert np.array_equal(got[~near], want[~near])
+        assert abs(count - rcount) <= int(near.sum())
+        assert 0.05 * mu.size < count < 0.95 * mu.size                  # the threshold really splits the set
+        assert lyr.snr_prune_count(thresh) == count
+
+
+def test_epoch_loop_vs_oracle(ctx):
+    """main:train (main.lua:13-53) over a shuffled epoch of a device-resident dataset --
+    the fused loop (vbnn_b200.train.train) against the ORACLE's train_epoch visiting the same shuffled order
+    with the device-drawn epsilon injected."""
+    import vbnn_b200
+    from vbnn_b200 import train as tr
+    from vbnn_b200 import _lib as L
+    over = dict(hidden=[32, 24], S=2, B=8.0, batchSize=50, testBatchSize=100, trainSize=400, testSize=200, mu_init=1,
+                var_init=0.01, log=False, testSamples=3, strict_reference=True, meanState=dict(learningRate=0.002))
+    opt = vbnn_b200.default_opt(**over)
+    ctx.set_step(0)
+    net = vbnn_b200.MLP(opt, ctx, max_batch=100)
+    oopt = O.default_opt(**over)
+    ref = O.MLPOracle(oopt, torch.float64, seed=3)
+    rng = np.random.RandomState(21)
+    for gl, ol in zip(net.model, ref.vb + [ref.out]):
+        if isinstance(ol, O.VBLinearOracle):
+            mu = rng.randn(ol.O, ol.I) * math.sqrt(2.0 / ol.I)
+            lv = rng.uniform(math.log(1e-4), math.log(1e-2), (ol.O, ol.I))
+            ol.means.copy_(torch.from_numpy(mu)); ol.lvars.copy_(torch.from_numpy(lv)); ol.compute_prior()
+            gl.set(L.BUF_MEANS, mu); gl.set(L.BUF_LVARS, lv); gl.compute_prior()
+        else:
+            w = rng.randn(*ol.weight.shape) * math.sqrt(2.0 / ol.weight.shape[1])
+            ol.weight.copy_(torch.from_numpy(w)); ol.bias.zero_()
+            gl.set(L.BUF_WEIGHT, w)
+    ds = tr.synthetic_dataset(400, 784, 10, seed=3, geometry=(28, 28))
+    ods = dict(inputs=ds["inputs"].double().cpu(), targets=ds["targets"].double().cpu())
+    # the same shuffled order main.lua:18 / utils.shuffle would visit
+    starts = torch.arange(0, 400, 50)
+    order = starts[torch.randperm(len(starts), generator=torch.Generator().manual_seed(1))].tolist()
+    eps_fn = lambda i: [[torch.from_numpy(cpu(net.model[k].draw_noise(i, s)).astype(np.float64)) for k in range(2)]
+                        for s in range(2)]                                # Philox step i = i-th visited minibatch
+    noise = [eps_fn(i) for i in range(len(order))]
+    acc, err = tr.train(net, ds, opt, fused=True, shuffle_seed=1)
+    racc, rerr = O.train_epoch(ref, ods, oopt, order, eps_fn=lambda i: noise[i])
+    assert abs(err - rerr) < 1e-4 * abs(rerr), (err, rerr)
+    assert abs(acc - racc) < 1e-2, (acc, racc)
+    for k in range(2):
+        assert rel(cpu(net.model[k].means), ref.vb[k].means.numpy()) < 2e-4
+        assert rel(cpu(net.model[k].lvars), ref.vb[k].lvars.numpy()) < 2e-4
+    assert rel(cpu(net.model[2].weight), ref.out.weight.numpy()) < 2e-4
+    # main:test (main.lua:55-74), MAP evaluation, against the oracle on the same rows
+    net.opt["quicktest"] = True; oopt["quicktest"] = True
+    tacc, terr = tr.test(net, dict(inputs=ds["inputs"][:200], targets=ds["targets"][:200]), opt)
+    e = a = 0.0
+    for t in range(0, 200, 100):
+        e_, a_ = ref.test(ods["inputs"][t:t + 100], ods["targets"][t:t + 100])
+        e += e_; a += a_
+    assert abs(terr - e / 2) < 1e-4 * abs(e / 2) and abs(tacc - a / 2) < 1e-2
+
+
+def test_checkpoint_files_and_metric_files(ctx, tmp_path):
+    """the files the reference's scripts read -- `parameters/means`, `parameters/vars`, `opt`
+    (mainviz.lua:12-15), `model` with `.old` rotation (utils.lua:73-80, main.lua:181) and the logger's per-id
+    metric files (logger.lua:18-26) carrying the 14 diagnostics of VBLinear.lua:150-163 -- written from device
+    state, read back, and resumed from (main.lua:146-148)."""
+    import vbnn_b200
+    from vbnn_b200 import checkpoint, logger, t7, train as tr
+    from vbnn_b200 import _lib as L
+    d = str(tmp_path / "exp")
+    over = dict(hidden=[32], S=2, B=8.0, batchSize=50, testBatchSize=100, trainSize=200, testSize=100, mu_init=1,
+                var_init=0.01, log=True, testSamples=2, network_name=d, meanState=dict(learningRate=0.002))
+    opt = vbnn_b200.default_opt(**over)
+    ctx.set_step(0)
+    net = vbnn_b200.MLP(opt, ctx, max_batch=100)
+    net.init_params(seed=4, he_means=True)
+    oopt = O.default_opt(**over)
+    ds = tr.synthetic_dataset(200, 784, 10, seed=3)
+    logger.init(d)
+    try:
+        r = tr.epoch(net, ds, dict(inputs=ds["inputs"][:100], targets=ds["targets"][:100]), opt, shuffle_seed=2)
+        # ---- metric files: one value per line; 14 ids x (4 minibatches x 1 VB layer) + 5 epoch metrics
+        for name in L.STAT_NAMES:
+            vals = logger.read_data(os.path.join(d, name))
+            assert len(vals) == 4 and all(math.isfinite(v) for v in vals), name
+        assert logger.read_data(os.path.join(d, "trainerr")) == [pytest.approx(r[1], rel=1e-12)]
+        assert logger.read_data(os.path.join(d, "devacc")) == [pytest.approx(r[2], rel=1e-12)]
+        assert logger.read_data(os.path.join(d, "lc")) == [pytest.approx(r[4], rel=1e-12)]
+        # 'var hat' of the last minibatch is compute_prior() of the parameters BEFORE its Adam step (VBLinear.lua:130,157)
+        assert logger.read_data(os.path.join(d, "min variance"))[-1] > 0
+    finally:
+        logger.Log.close(); logger.Log = None
+    # ---- parameters/means, parameters/vars, opt: what mainviz.lua:12-24 computes from them
+    checkpoint.save_parameters(net, d)
+    means = t7.load(os.path.join(d, "parameters", "means"))
+    vars_ = t7.load(os.path.join(d, "parameters", "vars"))
+    lopt = t7.load(os.path.join(d, "opt"))
+    assert means.dtype == np.float32 and means.shape == (32 * 784,) and vars_.shape == means.shape
+    assert np.array_equal(means, cpu(net.model[0].means).ravel())
+    assert rel(vars_, np.exp(cpu(net.model[0].lvars).astype(np.float64)).ravel()) < 1e-6
+    assert lopt["hidden"] == [32] and lopt["S"] == 2 and lopt["varState"]["learningRate"] == 0.05
+    _, count, _, _ = checkpoint.snr_pruned(means, vars_, 0.005)
+    assert abs(count - net.model[0].snr_prune_count(0.005)) <= 2
+    # ---- model (+ .old): resume is exact
+    assert os.path.isfile(os.path.join(d, "model"))
+    checkpoint.save_net(net, d)
+    assert os.path.isfile(os.path.join(d, "model.old"))
+    X, T = ds["inputs"][:50], ds["targets"][:50]
+    net.opt["log"] = False
+    ra = [net.train_step(X, T) for _ in range(2)]
+    net2 = vbnn_b200.MLP(vbnn_b200.default_opt(**dict(over, log=False)), ctx, max_batch=100)
+    checkpoint.load_net(net2, d)
+    rb = [net2.train_step(X, T) for _ in range(2)]
+    assert np.allclose(np.array(ra), np.array(rb), rtol=1e-6, atol=1e-7)
+    assert rel(cpu(net2.model[0].means), cpu(net.model[0].means)) < 1e-7
+
+
+@pytest.mark.parametrize("precision,reparam", [("fp32", "weight"), ("bf16", "local")])
+def test_submit_host_u8_equals_fp32_host_path(ctx, precision, reparam):
+    """The uint8 host format (MNIST bytes before data.lua:25 u.normalize; normalisation fused into the operand
+    staging on the device) gives the same minibatches as the fp32 host format fed (x - mean) * (1 / std)."""
+    sizes, N = [52, 48, 36, 6], 40                                       # 52 % 8 != 0: the ragged byte-row path too
+    rng = np.random.RandomState(31)
+    px = torch.from_numpy(rng.randint(0, 256, (N, sizes[0])).astype(np.uint8))
+    Th = torch.from_numpy(rng.randint(1, 7, N).astype(np.float32))
+    mean, std = 33.3, 78.6
+    inv = np.float32(1.0 / std)
+    Xf = ((px.float() - np.float32(mean)) * inv).contiguous().pin_memory()
+    res = []
+    for fmt in ("f32", "u8"):
+        ctx.set_step(3)
+        net, _, _, _ = build_pair(ctx, sizes, N, 2, 30.0, precision, reparam, seed=4, strict=False)
+        out = []
+        for _ in range(3):
+            if fmt == "f32":
+                net.submit_host(Xf, Th)
+            else:
+                net.submit_host_u8(px.pin_memory(), Th, mean, std)
+            out.append(net.collect())
+        res.append((out, cpu(net.model[0].means).copy(), cpu(net.model[1].lvars).copy()))
+    assert np.allclose(np.array(res[0][0]), np.array(res[1][0]), rtol=1e-6, atol=1e-7)
+    assert rel(res[1][1], res[0][1]) < 1e-7 and rel(res[1][2], res[0][2]) < 1e-7

@@ -89,6 +89,8 @@ _PROTOS = {
     "vbnn_mlp_step_host": (C.c_int, [_P, _P, _P, C.c_int, _F, _F]),
     "vbnn_mlp_submit_host": (C.c_int, [_P, _P, _P, C.c_int]),
     "vbnn_mlp_collect": (C.c_int, [_P, _F, _F]),
+    "vbnn_mlp_submit_host_u8": (C.c_int, [_P, _P, _P, C.c_int, C.c_float, C.c_float]),
+    "vbnn_mlp_join_streams": (C.c_int, [_P]),
     "vbnn_mlp_test": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _F, _F]),
     "vbnn_mlp_get_outputs": (C.c_int, [_P, C.c_int, _P]),
     "vbnn_mlp_launch_count": (C.c_int, [_P, C.POINTER(C.c_longlong)]),

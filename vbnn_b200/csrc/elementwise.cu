@@ -546,6 +546,51 @@ __global__ void __launch_bounds__(kThreads) k_cast(const float* src, int src_ld,
   }
 }
 
+// uint8 pixels -> normalised operands.  One thread = 8 consecutive columns (ld % 8 == 0): one 8-byte load when
+// the row pitch allows it, one 16-byte bf16 store.
+__global__ void __launch_bounds__(kThreads) k_cast_u8(const uint8_t* src, long long rows, int cols, float mean,
+                                                      float inv_std, bf16* dst, bf16* dst_sq, int ld,
+                                                      float* dst_f32, float* dst_sq_f32, int ld_f32) {
+  const int ldw = dst ? ld : ld_f32;
+  const int O = (ldw + 7) >> 3;
+  const long long octs = rows * O;
+  const bool vec = (cols & 7) == 0;
+  for (long long od = blockIdx.x * (long long)blockDim.x + threadIdx.x; od < octs;
+       od += (long long)gridDim.x * blockDim.x) {
+    const long long r = od / O;
+    const int c0 = (int)(od - r * O) * 8;
+    uint8_t b[8];
+    if (vec && c0 + 7 < cols) {
+      const uint2 t = *reinterpret_cast<const uint2*>(src + r * cols + c0);
+      *reinterpret_cast<uint2*>(b) = t;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = c0 + j < cols ? src[r * cols + c0 + j] : 0;
+    }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = c0 + j < cols ? ((float)b[j] - mean) * inv_std : 0.f;
+    if (dst) {
+      st4_bf16(dst + r * ld + c0, v[0], v[1], v[2], v[3]);
+      st4_bf16(dst + r * ld + c0 + 4, v[4], v[5], v[6], v[7]);
+      if (dst_sq) {
+        float w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float q = __bfloat162float(__float2bfloat16_rn(v[j])); w[j] = q * q; }
+        st4_bf16(dst_sq + r * ld + c0, w[0], w[1], w[2], w[3]);
+        st4_bf16(dst_sq + r * ld + c0 + 4, w[4], w[5], w[6], w[7]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j >= ld_f32) break;
+        dst_f32[r * ld_f32 + c0 + j] = v[j];
+        if (dst_sq_f32) dst_sq_f32[r * ld_f32 + c0 + j] = v[j] * v[j];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) k_square(const float* src, float* dst, long long n) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
@@ -809,6 +854,15 @@ int launch_colsum(const void* G, int is_bf16, long long rows, int cols, int ld, 
 int launch_cast(const float* src, int src_ld, long long rows, int cols, bf16* dst, bf16* dst_sq, int ld,
                 cudaStream_t st) {
   k_cast<<<grid_for(rows * (ld / 4)), kThreads, 0, st>>>(src, src_ld, rows, cols, dst, dst_sq, ld);
+  VB_CUDA(cudaGetLastError());
+  return VBNN_OK;
+}
+
+int launch_cast_u8(const uint8_t* src, long long rows, int cols, float mean, float inv_std, bf16* dst, bf16* dst_sq,
+                   int ld, float* dst_f32, float* dst_sq_f32, int ld_f32, cudaStream_t st) {
+  const int ldw = dst ? ld : ld_f32;
+  k_cast_u8<<<grid_for(rows * ((ldw + 7) / 8)), kThreads, 0, st>>>(src, rows, cols, mean, inv_std, dst, dst_sq, ld,
+                                                                  dst_f32, dst_sq_f32, ld_f32);
   VB_CUDA(cudaGetLastError());
   return VBNN_OK;
 }

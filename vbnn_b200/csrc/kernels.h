@@ -111,6 +111,10 @@ int launch_colsum(const void* G, int is_bf16, long long rows, int cols, int ld, 
 // fp32 [rows x cols] -> bf16 [rows x ld] (+ squared copy): tensor-core operand staging
 int launch_cast(const float* src, int src_ld, long long rows, int cols, bf16* dst, bf16* dst_sq,
                 int ld, cudaStream_t st);
+// uint8 [rows x cols] -> (x - mean) * inv_std as bf16 [rows x ld] (+ squared copy) or fp32 [rows x ld_f32]
+// (+ squared copy): data.lua's normalisation (utils.lua:29-35) fused into the operand staging
+int launch_cast_u8(const uint8_t* src, long long rows, int cols, float mean, float inv_std, bf16* dst, bf16* dst_sq,
+                   int ld, float* dst_f32, float* dst_sq_f32, int ld_f32, cudaStream_t st);
 // fp32 x -> x^2 (fp32 LRT path)
 int launch_square(const float* src, float* dst, long long n, cudaStream_t st);
 // fp32 exp() (sigma^2 operand of the fp32 LRT path / bf16 copies at init)

@@ -801,18 +801,24 @@ extern "C" int vbnn_layer_bind(vbnn_layer* L, int which, float* ptr) {
   VB_CHECK(ptr == nullptr || (reinterpret_cast<uintptr_t>(ptr) & 3) == 0, VBNN_E_INVALID, "vbnn_layer_bind: unaligned pointer");
   if (ptr == *slot) return VBNN_OK;
   cudaStream_t st = L->ctx->stream;
-  float* fresh = ptr;
-  if (!fresh) {                                   // hand the buffer back to the library
-    if (!*ext) return VBNN_OK;
-    VB_TRY(dev_alloc(&fresh, n));
+  if (ptr) {
+    // adopt the caller's tensor AS IS: Torch moved the values itself when it re-flattened the storage, and
+    // whatever the caller wrote since (mlp.lua:48-54 re-initialises weight / bias after getParameters) wins
+    if (!*ext) {
+      VB_CUDA(cudaStreamSynchronize(st));          // nothing of ours may still read the old buffer
+      cudaFree(*slot);
+    }
+    *slot = ptr;
+    *ext = true;
+    return VBNN_OK;
   }
+  if (!*ext) return VBNN_OK;
+  float* fresh = nullptr;                          // hand the buffer back to the library, contents kept
+  VB_TRY(dev_alloc(&fresh, n));
   VB_CUDA(cudaMemcpyAsync(fresh, *slot, n * 4, cudaMemcpyDeviceToDevice, st));
-  if (!*ext) {
-    VB_CUDA(cudaStreamSynchronize(st));           // the old buffer may still be read by the copy
-    cudaFree(*slot);
-  }
+  VB_CUDA(cudaStreamSynchronize(st));
   *slot = fresh;
-  *ext = ptr != nullptr;
+  *ext = false;
   return VBNN_OK;
 }
 

@@ -57,6 +57,22 @@ int stage_input(vbnn_mlp* m, const float* X, const float* T, int N) {
   return VBNN_OK;
 }
 
+// the same from uint8 pixels, data.lua's normalisation fused (vbnn_mlp_submit_host_u8)
+int stage_input_u8(vbnn_mlp* m, const uint8_t* X, const float* T, int N, float mean, float inv_std) {
+  cudaStream_t st = m->ctx->stream;
+  const int I0 = m->sizes[0], ld0 = m->ld[0];
+  if (m->bf16)
+    VB_TRY(launch_cast_u8(X, N, I0, mean, inv_std, (bf16*)m->act[0], m->lrt ? (bf16*)m->act2[0] : nullptr, ld0,
+                          nullptr, nullptr, 0, st));
+  else
+    VB_TRY(launch_cast_u8(X, N, I0, mean, inv_std, nullptr, nullptr, 0, (float*)m->act[0],
+                          m->lrt ? (float*)m->act2[0] : nullptr, ld0, st));
+  m->ctx->launches++;
+  if (T) VB_CUDA(cudaMemcpyAsync(m->targets, T, (size_t)N * 4, cudaMemcpyDeviceToDevice, st));
+  m->last_N = N;
+  return VBNN_OK;
+}
+
 // mlp:sample() for Zrun samples at once (mlp.lua:69-74 x main.lua:32-33)
 int sample_all(vbnn_mlp* m, int sample0, int Zrun) {
   for (vbnn_layer* L : m->layers) {
@@ -553,6 +569,7 @@ extern "C" int vbnn_mlp_destroy(vbnn_mlp* m) {
   if (m->t_list_dev) cudaFree(m->t_list_dev);
   for (int s = 0; s < 2; ++s) {
     if (m->xstage[s]) cudaFree(m->xstage[s]);
+    if (m->xstage_u8[s]) cudaFree(m->xstage_u8[s]);
     if (m->tstage[s]) cudaFree(m->tstage[s]);
     if (m->pipeline_ready) {
       cudaEventDestroy(m->slots[s].copied); cudaEventDestroy(m->slots[s].consumed); cudaEventDestroy(m->slots[s].done);
@@ -684,8 +701,9 @@ static int ensure_pipeline(vbnn_mlp* m) {
   return VBNN_OK;
 }
 
-extern "C" int vbnn_mlp_submit_host(vbnn_mlp* m, const float* X_host, const float* T_host, int N) {
-  VB_CHECK(m && X_host && T_host, VBNN_E_INVALID, "vbnn_mlp_submit_host: null argument");
+static int submit_host_any(vbnn_mlp* m, const float* X_host, const uint8_t* X8_host, const float* T_host, int N,
+                           float mean, float inv_std) {
+  VB_CHECK(m && (X_host || X8_host) && T_host, VBNN_E_INVALID, "vbnn_mlp_submit_host: null argument");
   VB_CHECK(N > 0 && N <= m->max_batch, VBNN_E_INVALID, "vbnn_mlp_submit_host: N=%d exceeds max_batch=%d", N, m->max_batch);
   VB_CUDA(cudaSetDevice(m->ctx->device));
   VB_TRY(ensure_pipeline(m));
@@ -693,20 +711,50 @@ extern "C" int vbnn_mlp_submit_host(vbnn_mlp* m, const float* X_host, const floa
   vbnn_ctx* c = m->ctx;
   const int s = m->submit_idx & 1;
   vbnn_mlp::Slot& sl = m->slots[s];
+  if (X8_host && !m->xstage_u8[s]) VB_TRY(dalloc(&m->xstage_u8[s], (size_t)m->max_batch * m->sizes[0]));
   // copy engine: wait until the previous user of this staging buffer has been consumed
   if (m->submit_idx >= 2) VB_CUDA(cudaStreamWaitEvent(c->copy_stream, sl.consumed, 0));
-  VB_CUDA(cudaMemcpyAsync(m->xstage[s], X_host, (size_t)N * m->sizes[0] * 4, cudaMemcpyHostToDevice, c->copy_stream));
+  if (X8_host)
+    VB_CUDA(cudaMemcpyAsync(m->xstage_u8[s], X8_host, (size_t)N * m->sizes[0], cudaMemcpyHostToDevice, c->copy_stream));
+  else
+    VB_CUDA(cudaMemcpyAsync(m->xstage[s], X_host, (size_t)N * m->sizes[0] * 4, cudaMemcpyHostToDevice, c->copy_stream));
   VB_CUDA(cudaMemcpyAsync(m->tstage[s], T_host, (size_t)N * 4, cudaMemcpyHostToDevice, c->copy_stream));
   VB_CUDA(cudaEventRecord(sl.copied, c->copy_stream));
   // compute stream
   VB_CUDA(cudaStreamWaitEvent(c->stream, sl.copied, 0));
-  VB_TRY(stage_input(m, m->xstage[s], m->tstage[s], N));
+  if (X8_host) VB_TRY(stage_input_u8(m, m->xstage_u8[s], m->tstage[s], N, mean, inv_std));
+  else VB_TRY(stage_input(m, m->xstage[s], m->tstage[s], N));
   VB_CUDA(cudaEventRecord(sl.consumed, c->stream));
   VB_TRY(step_enqueue(m, N));
   VB_CUDA(cudaMemcpyAsync(sl.h_result, m->result, 8, cudaMemcpyDeviceToHost, c->stream));
   VB_CUDA(cudaEventRecord(sl.done, c->stream));
   sl.busy = true; sl.N = N;
   m->submit_idx++; m->inflight++;
+  return VBNN_OK;
+}
+
+extern "C" int vbnn_mlp_submit_host(vbnn_mlp* m, const float* X_host, const float* T_host, int N) {
+  VB_CHECK(X_host, VBNN_E_INVALID, "vbnn_mlp_submit_host: null argument");
+  return submit_host_any(m, X_host, nullptr, T_host, N, 0.f, 1.f);
+}
+
+extern "C" int vbnn_mlp_submit_host_u8(vbnn_mlp* m, const uint8_t* X_host, const float* T_host, int N, float mean,
+                                       float inv_std) {
+  VB_CHECK(X_host, VBNN_E_INVALID, "vbnn_mlp_submit_host_u8: null argument");
+  return submit_host_any(m, nullptr, X_host, T_host, N, mean, inv_std);
+}
+
+extern "C" int vbnn_mlp_join_streams(vbnn_mlp* m) {
+  VB_CHECK(m, VBNN_E_INVALID, "null mlp");
+  vbnn_ctx* c = m->ctx;
+  if (m->peer && m->peer->active) {
+    VB_CUDA(cudaEventRecord(m->peer->ev_side, m->peer->side));
+    VB_CUDA(cudaStreamWaitEvent(c->stream, m->peer->ev_side, 0));
+  }
+  if (c->comm_stream && !m->ev_red.empty()) {
+    VB_CUDA(cudaEventRecord(m->ev_red[0], c->comm_stream));
+    VB_CUDA(cudaStreamWaitEvent(c->stream, m->ev_red[0], 0));
+  }
   return VBNN_OK;
 }
 

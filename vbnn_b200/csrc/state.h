@@ -116,6 +116,7 @@ struct vbnn_mlp {
   float* targets = nullptr;          // staged targets [N]
   float* xstage[2] = {nullptr, nullptr};   // fp32 H2D staging for the host-buffer API
   float* tstage[2] = {nullptr, nullptr};
+  uint8_t* xstage_u8[2] = {nullptr, nullptr};   // uint8 H2D staging (vbnn_mlp_submit_host_u8)
   float* result_acc = nullptr;       // [2*Z] loss sums / correct counts
   float* result = nullptr;           // [2] {error, accuracy}
   float* grad_arena = nullptr; size_t grad_count = 0;

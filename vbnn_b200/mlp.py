@@ -160,6 +160,24 @@ class MLP:
         L.check(L.lib().vbnn_mlp_submit_host(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
                                              x.shape[0]))
 
+    def submit_host_u8(self, pixels_host, targets_host, mean, std):
+        """The dataset's native bytes (MNIST pixels before data.lua:25 u.normalize): uint8 [N x input_size] host
+        tensor; (x - mean) / std is applied on the device while staging the GEMM operand."""
+        import torch
+        x = torch.as_tensor(pixels_host)
+        if x.dtype != torch.uint8 or x.is_cuda:
+            raise L.VbnnError(L.E_INVALID, "submit_host_u8 expects a uint8 host tensor")
+        x = x.reshape(x.shape[0], -1).contiguous()
+        t = torch.as_tensor(targets_host, dtype=torch.float32).reshape(-1).contiguous()
+        self._keep = getattr(self, "_keep", [])
+        self._keep.append((x, t))
+        self._keep = self._keep[-4:]
+        L.check(L.lib().vbnn_mlp_submit_host_u8(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(t.data_ptr()),
+                                                x.shape[0], C.c_float(mean), C.c_float(1.0 / std)))
+
+    def join_streams(self):
+        L.check(L.lib().vbnn_mlp_join_streams(self.handle))
+
     def collect(self):
         err, acc = C.c_float(), C.c_float()
         L.check(L.lib().vbnn_mlp_collect(self.handle, C.byref(err), C.byref(acc)))
