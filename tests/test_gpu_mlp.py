@@ -473,46 +473,70 @@ def test_c3_exact_size_properties(ctx):
                                                           ("weight", 1, 1, 0),   # EPI_FWD / EPI_DX / EPI_DW pair tiles
                                                           ("weight", 3, 1, 0)])  # multi-sample dW, global accumulate
 def test_pair_tile_epilogues_vs_oracle(ctx, reparam, S, lrt_split, dw_split):
+    """Two checks per tensor: (1) against the bf16-rounding oracle at the tolerance of the other bf16 tests;
+    (2) against THIS library's default tiling (128 x 128 single-CTA tiles at this size, oracle-checked by the tests
+    above) on the same inputs and noise -- identical rounding points, so only fp32 summation order differs: <= 1e-3,
+    whole tensor and per 64-row / 64-column band (a wrong 32-column chunk or a row offset in ONE CTA of the pair would
+    be diluted in the Frobenius norm of the whole matrix, not in its band)."""
     import vbnn_b200
     sizes, N = [600, 552, 530, 10], 540
-    old = [vbnn_b200.knob("tc_bn", 256), vbnn_b200.knob("tc_cg", 2), vbnn_b200.knob("lrt_split", lrt_split),
-           vbnn_b200.knob("dw_split", dw_split)]
-    try:
-        net, ref, gopt, oopt = build_pair(ctx, sizes, N, S, 30.0, "bf16", reparam, seed=7, strict=False,
-                                          operand_round=O.round_bf16)
-        rng = np.random.RandomState(17)
-        nvb = len(ref.vb_all)
-        for it in range(2):                       # second minibatch: graph replay + Adam state carried over
-            Xn = rng.randn(N, sizes[0]); Tn = rng.randint(1, sizes[-1] + 1, N).astype(np.float64)
-            step = ctx.get_step()
-            noise = [[torch.from_numpy(cpu(net.model[k].draw_noise(step, s, rows=N)).astype(np.float64))
-                      for k in range(nvb)] for s in range(S)]
-            err, acc = net.train_step(torch.from_numpy(Xn).float().cuda(), torch.from_numpy(Tn).float().cuda())
-            kw = dict(zeta=noise) if reparam == "local" else dict(eps=noise)
-            rerr, racc, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), **kw)
-            assert abs(err - rerr) < 2e-3 * abs(rerr), (it, err, rerr)
-            for k, ol in enumerate(ref.vb_all):
-                gl = net.model[k]
-                gw, gs, gb = accs[k]
-                # per 64-row band as well as whole-tensor: a wrong 32-column chunk or a row offset in ONE CTA
-                # of the pair would be diluted in the Frobenius norm of the whole matrix, not in its band
-                G, Gr = cpu(gl.gradWeight), gw.numpy()
-                S_, Sr = cpu(gl.gradSum), gs.numpy()
-                assert rel(G, Gr) < 5e-3 and rel(S_, Sr) < 1e-2, (it, k)
-                for r0 in range(0, G.shape[0], 64):
-                    assert rel(G[r0:r0 + 64], Gr[r0:r0 + 64]) < 1e-2, (it, k, "gW rows", r0)
-                    assert rel(S_[r0:r0 + 64], Sr[r0:r0 + 64]) < 2e-2, (it, k, "gS rows", r0)
-                for c0 in range(0, G.shape[1], 64):
-                    assert rel(G[:, c0:c0 + 64], Gr[:, c0:c0 + 64]) < 1e-2, (it, k, "gW cols", c0)
-                    assert rel(S_[:, c0:c0 + 64], Sr[:, c0:c0 + 64]) < 2e-2, (it, k, "gS cols", c0)
-                assert rel(cpu(gl.gradBias), gb.numpy()) < 5e-3, (it, k, "gb")
-                assert rel(cpu(gl.means), ol.means.numpy()) < 5e-3, (it, k, "means")
-                assert rel(cpu(gl.lvars), ol.lvars.numpy()) < 5e-3, (it, k, "lvars")
-            assert rel(cpu(net.model[-1].weight), ref.out.weight.numpy()) < 5e-3
-            assert rel(cpu(net.model[-1].gradWeight), ref.out.gradWeight.numpy()) < 5e-3
-    finally:
-        for name, v in zip(("tc_bn", "tc_cg", "lrt_split", "dw_split"), old):
-            vbnn_b200.knob(name, v)
+    names = ("tc_bn", "tc_cg", "lrt_split", "dw_split")
+    lrt = reparam == "local"
+    rng = np.random.RandomState(17)
+    data = [(rng.randn(N, sizes[0]), rng.randint(1, sizes[-1] + 1, N).astype(np.float64)) for _ in range(2)]
+    runs = {}
+    for forced in (False, True):
+        old = [vbnn_b200.knob(n) for n in names]
+        if forced:
+            for n, v in zip(names, (256, 2, lrt_split, dw_split)):
+                vbnn_b200.knob(n, v)
+        try:
+            ctx.set_step(40)
+            net, ref, gopt, oopt = build_pair(ctx, sizes, N, S, 30.0, "bf16", reparam, seed=7, strict=False,
+                                              operand_round=O.round_bf16)
+            nvb = len(ref.vb_all)
+            trace = []
+            for it, (Xn, Tn) in enumerate(data):      # second minibatch: graph replay + Adam state carried over
+                step = ctx.get_step()
+                noise = [[torch.from_numpy(cpu(net.model[k].draw_noise(step, s, rows=N)).astype(np.float64))
+                          for k in range(nvb)] for s in range(S)]
+                err, acc = net.train_step(torch.from_numpy(Xn).float().cuda(), torch.from_numpy(Tn).float().cuda())
+                kw = dict(zeta=noise) if lrt else dict(eps=noise)
+                rerr, racc, accs = oracle_step(ref, oopt, torch.from_numpy(Xn), torch.from_numpy(Tn), **kw)
+                assert abs(err - rerr) < 5e-3 * abs(rerr), (forced, it, err, rerr)
+                snap = dict(err=err)
+                for k, ol in enumerate(ref.vb_all):
+                    gl = net.model[k]
+                    gw, gs, gb = accs[k]
+                    snap[k] = dict(gW=cpu(gl.gradWeight).copy(), gS=cpu(gl.gradSum).copy(), gb=cpu(gl.gradBias).copy(),
+                                   mu=cpu(gl.means).copy(), lv=cpu(gl.lvars).copy())
+                    assert rel(snap[k]["gW"], gw.numpy()) < (5e-3 if lrt else 1e-2), (forced, it, k, "gW vs oracle")
+                    assert rel(snap[k]["gS"], gs.numpy()) < (1e-2 if lrt else 2e-2), (forced, it, k, "gS vs oracle")
+                    assert rel(snap[k]["gb"], gb.numpy()) < 1e-2, (forced, it, k, "gb vs oracle")
+                    assert rel(snap[k]["mu"], ol.means.numpy()) < 5e-3, (forced, it, k, "means vs oracle")
+                    assert rel(snap[k]["lv"], ol.lvars.numpy()) < 5e-3, (forced, it, k, "lvars vs oracle")
+                snap["out_w"] = cpu(net.model[-1].weight).copy(); snap["out_gw"] = cpu(net.model[-1].gradWeight).copy()
+                assert rel(snap["out_w"], ref.out.weight.numpy()) < 5e-3
+                assert rel(snap["out_gw"], ref.out.gradWeight.numpy()) < 1e-2
+                trace.append(snap)
+            runs[forced] = trace
+            del net
+        finally:
+            for n, v in zip(names, old):
+                vbnn_b200.knob(n, v)
+    for it in range(2):
+        a, b = runs[True][it], runs[False][it]
+        assert abs(a["err"] - b["err"]) < 1e-4 * abs(b["err"]), (it, a["err"], b["err"])
+        for k in range(2):
+            for name in ("gW", "gS", "gb", "mu", "lv"):
+                A, B = a[k][name], b[k][name]
+                assert rel(A, B) < 1e-3, (it, k, name, rel(A, B))
+                if A.ndim == 2 and name in ("gW", "gS"):
+                    for r0 in range(0, A.shape[0], 64):
+                        assert rel(A[r0:r0 + 64], B[r0:r0 + 64]) < 3e-3, (it, k, name, "rows", r0)
+                    for c0 in range(0, A.shape[1], 64):
+                        assert rel(A[:, c0:c0 + 64], B[:, c0:c0 + 64]) < 3e-3, (it, k, name, "cols", c0)
+        assert rel(a["out_w"], b["out_w"]) < 1e-4 and rel(a["out_gw"], b["out_gw"]) < 1e-3
 
 
 @pytest.mark.parametrize("M,N,K", [(540, 600, 552), (530, 552, 540)])

@@ -1,3 +1,20 @@
-import json,sys
-d=json.loads(sys.stdin.readline())
-print(d["config"].get("dp_exchange"), round(d["value"]), round(d["ms_per_step"],3), d["clocks"]["sm_mhz"], {k:(round(v["tflops"]),round(v["ms_per_step"],3)) for k,v in d["roofline"]["per_class"].items()}, {k:round(v,3) for k,v in d.get("phases_ms_per_step",{}).items()})
+"""Pretty-print the JSON line(s) bench.py / tools/c5_sweep.py wrote to a file:  python tools/show_bench.py FILE"""
+import json
+import sys
+
+
+def show(d, ind=0):
+    for k, v in d.items():
+        if isinstance(v, dict) and any(isinstance(x, dict) for x in v.values()) or k in (
+                "roofline", "roofline_hbm", "e2e", "e2e_u8", "cpu_baseline", "phases_ms_per_step", "clocks", "dp_parity"):
+            print(" " * ind + k + ":")
+            show(v, ind + 2)
+        else:
+            s = json.dumps(v)
+            print(" " * ind + f"{k}: {s[:170]}")
+
+
+for line in open(sys.argv[1]):
+    if line.startswith("{"):
+        show(json.loads(line))
+        print()
