@@ -301,9 +301,12 @@ class Env:
         return [bytes(o.cpu().tolist()) for o in out]
 
     def barrier(self):
+        """Every rank first drains ALL of its own streams (the peer-mode side stream included), then meets the
+        others: after the barrier nobody's device still writes into a peer's buffers."""
+        self.torch.cuda.synchronize()
         if self.dist is not None:
             self.dist.barrier()
-        self.torch.cuda.synchronize()
+            self.torch.cuda.synchronize()
 
     def max_over_ranks(self, ms):
         if self.dist is None:
@@ -517,7 +520,7 @@ def dp_parity_check(env):
     Xl, Tl = X[lo:lo + n_loc].cuda(), T[lo:lo + n_loc].cuda()
     for _ in range(steps):
         net.train_step(Xl, Tl)
-    env.ctx.synchronize(); env.barrier()
+    env.barrier()                                                       # all streams of all ranks drained
     net.sync_replicas()
     env.barrier()
     adam_ids = (VL.BUF_ADAM_M_MU, VL.BUF_ADAM_V_MU, VL.BUF_ADAM_M_VAR, VL.BUF_ADAM_V_VAR)

@@ -282,8 +282,11 @@ int vbnn_comm_allreduce(vbnn_ctx* ctx, float* buf_dev, size_t count);
 int vbnn_mlp_peer_export(vbnn_mlp* mlp, void* blob, size_t capacity, size_t* blob_len);
 int vbnn_mlp_peer_import(vbnn_mlp* mlp, const void* blobs_all_ranks, size_t blob_len);
 int vbnn_mlp_peer_active(const vbnn_mlp* mlp);
-/* collective (host barrier before and after): refresh the fp32 state of rows owned by other ranks
- * (Adam moments, and whatever training does not push) before get / checkpoint / clamp_to_map */
+/* collective: refresh the fp32 state of rows owned by other ranks (Adam moments, and whatever training does
+ * not push) before get / checkpoint / clamp_to_map.  Protocol, on EVERY rank: drain the device
+ * (cudaDeviceSynchronize: the last minibatch's shard updates run on the library's side stream) -> host barrier
+ * -> vbnn_mlp_sync_replicas -> host barrier.  A rank that pulls before its peer has drained reads rows one
+ * optimiser step behind. */
 int vbnn_mlp_sync_replicas(vbnn_mlp* mlp);
 /* shard of an O-row matrix owned by `rank`; returns rows per owner (a multiple of 32) */
 int vbnn_peer_shard(int O, int nranks, int rank, int* row0, int* rows);

@@ -9,7 +9,11 @@ step counters per rank (mseq on the main stream, sseq on the side stream):
 
   grad_ready[q][j][r] = t   raised on q by r's main stream after its dW_j(t)
   param_ready[r][j][q] = t  raised on r by q's side stream after its pushes of layer j, step t
-  main stream, start of step t : waits param_ready[r][j][q] >= t-1 for all j, q
+  main stream, step t, before forward_j : waits param_ready[r][j][q] >= t-1 for all q (PER LAYER, right before
+                                         layer j's operands are first read)
+  main stream, backward of step t      : the backward-data chain dX_{L-1} .. dX_1 first, then the parameter-gradient
+                                         GEMMs dW_0 .. dW_{L-1} in FORWARD order, so the layer the next forward needs
+                                         first finishes its exchange first and the tail belongs to the last layer
   side stream, layer j, step t : starts after the own dW_j(t) (event), waits grad_ready[q][j][r] >= t for all r
 
 This test replays that protocol as 2G sequential "streams" under random interleavings and asserts the data
@@ -38,17 +42,20 @@ class Model:
     def main_stream(self, r):
         G, L = self.G, self.L
         for t in range(1, self.T + 1):
-            yield ("wait", lambda t=t: all(self.param_ready[r][j][q] >= t - 1 for j in range(L) for q in range(G)))
-            for j in range(L):                                     # forward
+            for j in range(L):                                     # forward, per-layer wait
+                yield ("wait", lambda j=j, t=t: all(self.param_ready[r][j][q] >= t - 1 for q in range(G)))
                 def fwd(j=j, t=t):
                     assert all(v == t - 1 for v in self.operand_version[r][j]), ("forward saw stale/new operands", r, j, t)
                 yield ("do", fwd)
-            for j in range(L - 1, -1, -1):                         # backward: dX_j then dW_j
+            for j in range(L - 1, 0, -1):                          # backward-data chain (layer 0's is skipped)
                 def dx(j=j, t=t):
                     assert all(v == t - 1 for v in self.operand_version[r][j]), ("backward-data saw wrong operands", r, j, t)
                     self.reading_until[r][j] = t
                 yield ("do", dx)
+            for j in range(L):                                     # parameter gradients in forward order
                 def dw(j=j, t=t):
+                    if j == 0:
+                        self.reading_until[r][0] = t               # layer 0's operands were last read by its forward
                     for q in range(G):                             # reduce-scatter fused into the epilogue
                         assert self.slot_read[q][j] >= t - 1, ("slot overwritten before the owner consumed it", r, q, j, t)
                         self.slot_version[q][j][r] = t
@@ -62,7 +69,7 @@ class Model:
     def side_stream(self, q):
         G, L = self.G, self.L
         for t in range(1, self.T + 1):
-            for j in range(L - 1, -1, -1):
+            for j in range(L):
                 yield ("wait", lambda j=j, t=t: self.dw_done[q][j] >= t)                       # cudaStreamWaitEvent(ev_dw)
                 yield ("wait", lambda j=j, t=t: all(self.grad_ready[q][j][r] >= t for r in range(G)))
                 def update(j=j, t=t):
@@ -108,7 +115,7 @@ def test_peer_protocol_has_no_hazard_or_deadlock(G, L):
 
 
 def test_model_detects_a_missing_wait():
-    """Sanity of the checker itself: without the start-of-step wait a fast rank's next forward must trip
+    """Sanity of the checker itself: without the per-layer waits a fast rank's next forward must trip
     one of the assertions under some interleaving."""
     class Broken(Model):
         def main_stream(self, r):

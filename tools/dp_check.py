@@ -59,9 +59,9 @@ def main():
         for it in range(3):
             net.train_step(X[rank * n_loc:(rank + 1) * n_loc].cuda(), T[rank * n_loc:(rank + 1) * n_loc].cuda())
         if use_peer:
-            ctx_dp.synchronize(); dist.barrier()
+            torch.cuda.synchronize(); dist.barrier()      # every rank's side stream has finished its last shard update
             net.sync_replicas()
-            dist.barrier()
+            torch.cuda.synchronize(); dist.barrier()
         dp = [m.means.clone() for m in net.model[:-1]] + [net.model[-1].weight.clone()]
         dp_lv = [m.lvars.clone() for m in net.model[:-1]]
         from vbnn_b200 import _lib as VL
@@ -94,7 +94,7 @@ def main():
                     ok &= e < 10 * tol
             assert all(m.t == 3 for m in net.model)
             torch.cuda.set_stream(ctx_dp.stream)
-        ctx_dp.synchronize(); dist.barrier()          # nobody still writes into a peer's buffers
+        torch.cuda.synchronize(); dist.barrier()      # nobody still writes into a peer's buffers
         del net
         dist.barrier()
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{lr}")

@@ -16,16 +16,15 @@ const Entry kTable[] = {
     {"tc_bn", &Knobs::tc_bn},           {"tc_cg", &Knobs::tc_cg},         {"tc_gm", &Knobs::tc_gm},
     {"tc_clc", &Knobs::tc_clc},         {"tc_staged", &Knobs::tc_staged}, {"tc_tacc", &Knobs::tc_tacc},
     {"tc_dw64", &Knobs::tc_dw64},       {"lrt_split", &Knobs::lrt_split}, {"dw_split", &Knobs::dw_split},
-    {"dp_overlap", &Knobs::dp_overlap}, {"no_graph", &Knobs::no_graph},   {"peer_l0_push", &Knobs::peer_l0_push},
+    {"dp_overlap", &Knobs::dp_overlap}, {"no_graph", &Knobs::no_graph},   {"peer_fused_push", &Knobs::peer_fused_push},
 };
 
-// VBNN_<NAME>; VBNN_PEER_L0_PUSH also accepts the historical spelling "ce" (= 0)
+// VBNN_<NAME>
 bool from_env(const Entry& e, int* out) {
   std::string var = "VBNN_";
   for (const char* c = e.name; *c; ++c) var += (char)(*c >= 'a' && *c <= 'z' ? *c - 32 : *c);
   const char* v = getenv(var.c_str());
   if (!v || !*v) return false;
-  if (!strcmp(e.name, "peer_l0_push") && !strcmp(v, "ce")) { *out = 0; return true; }
   *out = atoi(v);
   return true;
 }

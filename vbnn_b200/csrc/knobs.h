@@ -20,7 +20,7 @@ struct Knobs {
   int dw_split = -1;    // LRT dW as two single-accumulator GEMMs: -1 = only in peer mode
   int dp_overlap = 1;   // NCCL mode: per-layer allreduce overlapped with backward
   int no_graph = 0;     // eager launches instead of CUDA graph replay
-  int peer_l0_push = 1; // layer 0's all-gather: 1 = fused NVLink stores, 0 = copy engines
+  int peer_fused_push = 0; // operand all-gather: 0 = copy engines (SM-free), 1 = NVLink stores from the update kernel
 };
 
 Knobs& knobs();

@@ -196,13 +196,11 @@ int loss_all(vbnn_mlp* m, int N, int Zrun, bool backward, float* logp_out, float
   return VBNN_OK;
 }
 
-// model:backward for layer j (mlp.lua:79): updateGradInput (skipped for the first layer, whose
-// gradInput nobody reads) + accGradParameters.
-int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumulate, bool scatter = false) {
+// updateGradInput of layer j (its gradInput is layer j-1's gradOutput, ReLU backward fused)
+int backward_data_layer(vbnn_mlp* m, int j, int N, int Zrun) {
   vbnn_layer* L = m->layers[j];
   const bool lrt = layer_lrt(L);
   const int ldi = m->ld[j], ldo = m->ld[j + 1];
-  const long long zs_in = j == 0 ? 0 : (long long)N * ldi;
   const long long zs_out = (long long)N * ldo;
   const bool w_batched = L->kind == VBNN_KIND_VB && !lrt;
   cudaStream_t st = m->ctx->stream;
@@ -256,6 +254,17 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
       VB_TRY(gemm_simt_launch(mode, g, p, Zrun, st, &m->ctx->launches));
     }
   }
+  return VBNN_OK;
+}
+
+// accGradParameters of layer j (+ gradBias column sums)
+int backward_weight_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumulate, bool scatter = false) {
+  vbnn_layer* L = m->layers[j];
+  const bool lrt = layer_lrt(L);
+  const int ldi = m->ld[j], ldo = m->ld[j + 1];
+  const long long zs_in = j == 0 ? 0 : (long long)N * ldi;
+  const long long zs_out = (long long)N * ldo;
+  cudaStream_t st = m->ctx->stream;
   {
     EpiParams p;
     memset(&p, 0, sizeof(p));
@@ -328,30 +337,54 @@ int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumul
   return VBNN_OK;
 }
 
-// reduce_overlap: data-parallel step -- the allreduce of layer j's {gW, gS, gb} slice starts on the
-// communication stream as soon as its dW is done and overlaps the backward of the layers below.
+// model:backward for layer j (mlp.lua:79): updateGradInput (skipped for the first layer, whose
+// gradInput nobody reads) + accGradParameters.
+int backward_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int accumulate) {
+  VB_TRY(backward_data_layer(m, j, N, Zrun));
+  return backward_weight_layer(m, j, N, Zrun, sample0, accumulate, false);
+}
+
 int run_samples(vbnn_mlp* m, int N, int Zrun, int sample0, int accumulate, bool backward, bool reduce_overlap = false,
                 bool peer = false) {
   const int Lc = nlayers(m);
   vbnn_ctx* c = m->ctx;
-  for (int j = 0; j < Lc; ++j) VB_TRY(forward_layer(m, j, N, Zrun, sample0, false));
-  VB_TRY(prof_mark(c, 3));
+  for (int j = 0; j < Lc; ++j) {
+    // peer mode: layer j's operands of the previous minibatch must have landed from every owner -- waited for
+    // per layer, right before they are first read, so that the exchange of the layers updated last (see the
+    // backward order below) hides behind the forward GEMMs of the layers before them
+    if (peer) { VB_TRY(peer_wait_params(m, j)); VB_TRY(prof_mark(c, 1)); }
+    VB_TRY(forward_layer(m, j, N, Zrun, sample0, false));
+    VB_TRY(prof_mark(c, 3));
+  }
   VB_TRY(loss_all(m, N, Zrun, backward, nullptr, m->result_acc));
   VB_TRY(prof_mark(c, 4));
-  if (backward)
-    for (int j = Lc - 1; j >= 0; --j) {
-      VB_TRY(backward_layer(m, j, N, Zrun, sample0, accumulate, peer));
+  if (!backward) return VBNN_OK;
+  if (peer) {
+    // Peer mode runs the backward-data chain first and the parameter-gradient GEMMs afterwards in FORWARD order
+    // (same GEMMs, same operands: G_j / H_j stay in their per-layer buffers).  Layer 0 -- the first one the next
+    // minibatch's forward needs -- then finishes its exchange (reduce-scatter in the dW epilogue, owner update,
+    // operand all-gather on the side stream) while the dW GEMMs of the layers above still run, and the tail
+    // after the last dW belongs to the output layer, which the next forward reads last.
+    for (int j = Lc - 1; j >= 1; --j) { VB_TRY(backward_data_layer(m, j, N, Zrun)); VB_TRY(prof_mark(c, 5)); }
+    for (int j = 0; j < Lc; ++j) {
+      VB_TRY(backward_weight_layer(m, j, N, Zrun, sample0, accumulate, true));
       VB_TRY(prof_mark(c, 5));
-      // peer mode: signal, then the owner update + all-gather of layer j run on the side stream while
-      // this stream continues with the layers below
-      if (peer) VB_TRY(peer_after_dw(m, j));
-      if (reduce_overlap) {
-        VB_CUDA(cudaEventRecord(m->ev_bwd[j], c->stream));
-        VB_CUDA(cudaStreamWaitEvent(c->comm_stream, m->ev_bwd[j], 0));
-        VB_TRY(comm_allreduce_internal(c, m->grad_arena + m->grad_off[j], m->grad_len[j], c->comm_stream));
-        VB_CUDA(cudaEventRecord(m->ev_red[j], c->comm_stream));
-      }
+      VB_TRY(peer_after_dw(m, j));       // signal; owner update + all-gather of layer j on the side stream
     }
+    return VBNN_OK;
+  }
+  for (int j = Lc - 1; j >= 0; --j) {
+    VB_TRY(backward_layer(m, j, N, Zrun, sample0, accumulate));
+    VB_TRY(prof_mark(c, 5));
+    // reduce_overlap: the allreduce of layer j's {gW, gS, gb} slice starts on the communication stream as soon as
+    // its dW is done and overlaps the backward of the layers below
+    if (reduce_overlap) {
+      VB_CUDA(cudaEventRecord(m->ev_bwd[j], c->stream));
+      VB_CUDA(cudaStreamWaitEvent(c->comm_stream, m->ev_bwd[j], 0));
+      VB_TRY(comm_allreduce_internal(c, m->grad_arena + m->grad_off[j], m->grad_len[j], c->comm_stream));
+      VB_CUDA(cudaEventRecord(m->ev_red[j], c->comm_stream));
+    }
+  }
   return VBNN_OK;
 }
 
@@ -386,8 +419,10 @@ int step_body(vbnn_mlp* m, int N) {
   if (m->peer && m->peer->active) {
     // data parallel over NVLink peer memory (peer.cu): no collective call anywhere in the step
     VB_TRY(peer_check(m));
-    VB_TRY(peer_wait_params(m));                     // last step's operands from every owner have landed
-    VB_TRY(prof_mark(m->ctx, 1));
+    if (!m->lrt) {                                   // weight sampling reads mu / log sigma^2 of every layer up front
+      VB_TRY(peer_wait_params(m, -1));
+      VB_TRY(prof_mark(m->ctx, 1));
+    }
     VB_TRY(sample_all(m, 0, m->Z));
     VB_TRY(prof_mark(m->ctx, 2));
     VB_TRY(run_samples(m, N, m->Z, 0, 0, true, false, true));
@@ -788,7 +823,7 @@ extern "C" int vbnn_mlp_test(vbnn_mlp* m, const float* X, const float* T, int N,
   if (m->peer && m->peer->active) {
     VB_CHECK(n_samples > 0 || !m->peer->stale, VBNN_E_STATE,
              "vbnn_mlp_test(quicktest) in peer mode: call vbnn_mlp_sync_replicas on every rank first");
-    VB_TRY(peer_wait_params(m));
+    VB_TRY(peer_wait_params(m, -1));
   }
   const int Lc = nlayers(m);
   int total = 0;

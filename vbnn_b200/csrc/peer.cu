@@ -198,11 +198,12 @@ void peer_scatter(const vbnn_mlp* m, int j, EpiParams& p) {
   }
 }
 
-int peer_wait_params(vbnn_mlp* m) {
+int peer_wait_params(vbnn_mlp* m, int j) {
   vbnn_peer* P = m->peer;
   const int Lc = (int)m->layers.size();
-  k_wait_params<<<1, 256, 0, m->ctx->stream>>>(reinterpret_cast<const uint32_t*>(P->block + P->off_param_ready), P->seq,
-                                               Lc, P->G, P->d_err);
+  const uint32_t* ready = reinterpret_cast<const uint32_t*>(P->block + P->off_param_ready);
+  if (j < 0) k_wait_params<<<1, 256, 0, m->ctx->stream>>>(ready, P->seq, Lc, P->G, P->d_err);
+  else k_wait_params<<<1, 32, 0, m->ctx->stream>>>(ready + (size_t)j * P->G, P->seq + 2 * j, 1, P->G, P->d_err);
   VB_CUDA(cudaGetLastError());
   m->ctx->launches++;
   return VBNN_OK;
@@ -261,11 +262,10 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     u.partials = L->prior_partials; u.n_partials = L->n_part;
     u.next_partials = L->prior_partials; u.partials_pingpong = 1;
     u.grid_override = gq; u.part_off = me * gq;
-    // Layers > 0 are updated while the persistent GEMM CTAs of the layers below own every SM: use the
-    // 128-thread / 80-register variant that fits beside them (a full-width kernel would only start at
-    // the next kernel boundary and push the whole chain into the tail of the minibatch).  Layer 0's
-    // update runs after the last GEMM: full width.
-    u.coresident = j > 0 ? 1 : 0;
+    // The shard updates run while the persistent GEMM CTAs of the main stream (the dW GEMMs of the layers above,
+    // then the next minibatch's forward) own every SM: use the 128-thread / 80-register variant that fits beside
+    // them (a full-width kernel would only start at the next kernel boundary and stall the whole chain).
+    u.coresident = 1;
     for (int q = 0; q < G; ++q)
       if (q != me) u.peer_partials[u.n_peer++] = (double*)pl.partials.ptr[q];
     u.var_hat_dev = L->var_hat_dev; u.t_dev = L->t_dev;
@@ -273,10 +273,11 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     u.lr_mu = L->opts.lr_mu; u.lr_var = L->opts.lr_var;
     u.beta1 = L->opts.adam_beta1; u.beta2 = L->opts.adam_beta2; u.eps = L->opts.adam_eps;
     u.lrt = layer_lrt(L);
-    const bool fused_push = j == 0 && knobs().peer_l0_push && pl.rows > 0;
+    // knob peer_fused_push: the update kernel stores the refreshed operands to every rank itself instead of
+    // 2 x (G-1) copy-engine copies.  It paid when layer 0's update was the tail of the minibatch (idle SMs); with
+    // the dW GEMMs issued in forward order every update runs under GEMMs, where SM-free copy engines win.
+    const bool fused_push = knobs().peer_fused_push != 0 && pl.rows > 0;
     if (fused_push) {
-      // layer 0: its update is the tail of the minibatch -- the SMs and NVLink are otherwise idle, so the
-      // kernel stores the refreshed operands to every rank itself instead of 2 x (G-1) serial copies
       for (int q = 0; q < G; ++q) {
         if (q == me) continue;
         const int i = u.n_push++;

@@ -146,7 +146,7 @@ int comm_allreduce_internal(vbnn_ctx* ctx, float* buf, size_t count, cudaStream_
 // peer mode (peer.cu)
 void peer_destroy(vbnn_mlp* m);
 void peer_scatter(const vbnn_mlp* m, int j, EpiParams& p);                // dW epilogue -> owners' slots
-int peer_wait_params(vbnn_mlp* m);                                        // main stream, before forward
+int peer_wait_params(vbnn_mlp* m, int j);                                 // main stream, before layer j's forward (-1: all layers)
 int peer_after_dw(vbnn_mlp* m, int j);                                    // signal + owner update + push
 int peer_check(vbnn_mlp* m);                                              // host: a peer wait timed out?
 // tensor-core GEMM launch with optional event bracketing (ctx->profiling)
