@@ -499,11 +499,12 @@ def roofline_objects(m, w, N, steps, peaks, is_c3=False):
 
 
 def dp_parity_check(env):
-    """Data-parallel vs single-GPU parity on the exact path the scaling run times: the C3 network (4096 wide: 256 x 256
-    CTA-pair tiles, dW tiles scattered into every owner's slot, co-resident shard updates, fused layer-0 push), 1024 rows
-    per rank, 3 minibatches.  After sync_replicas every rank must hold -- parameters AND Adam state -- what ONE GPU stepping
-    the whole global minibatch holds (identical Philox noise: zeta is indexed by the global row).  Differences are fp32
-    summation order only (rows summed per rank, then across ranks)."""
+    """Data-parallel vs single-GPU parity on the exact paths the scaling runs time: the C3 network (4096 wide: 256 x 256
+    CTA-pair tiles, co-resident shard updates, copy-engine operand all-gather), 1024 rows per rank, 3 minibatches, once
+    per gradient transport -- dW tiles stored into every owner's slot from the epilogue ("fused", what the weak-scaling
+    run uses) and staged locally + moved by the copy engines ("ce", what the strong-scaling run uses).  After
+    sync_replicas every rank must hold -- parameters AND Adam state -- what ONE GPU stepping the whole global minibatch
+    holds (identical Philox noise: zeta is indexed by the global row).  Differences are fp32 summation order only."""
     torch, dist = env.torch, env.dist
     import vbnn_b200
     from vbnn_b200 import _lib as VL
@@ -513,50 +514,60 @@ def dp_parity_check(env):
     g = torch.Generator().manual_seed(11)
     X = torch.randn(Ng, w["sizes"][0], generator=g)
     T = torch.randint(1, w["sizes"][-1] + 1, (Ng,), generator=g).float()
-    net, _ = env.make_net(w, n_loc)
-    env.ctx.set_step(7)
-    env.barrier()
-    lo = env.rank * n_loc
-    Xl, Tl = X[lo:lo + n_loc].cuda(), T[lo:lo + n_loc].cuda()
-    for _ in range(steps):
-        net.train_step(Xl, Tl)
-    env.barrier()                                                       # all streams of all ranks drained
-    net.sync_replicas()
-    env.barrier()
     adam_ids = (VL.BUF_ADAM_M_MU, VL.BUF_ADAM_V_MU, VL.BUF_ADAM_M_VAR, VL.BUF_ADAM_V_VAR)
-    same = True
-    for m in net.model[:-1]:                                            # every rank holds identical parameters
-        t = m.means.clone(); ref = t.clone(); dist.broadcast(ref, 0)
-        same &= bool(torch.equal(ref, t))
-    flag = torch.tensor([1 if same else 0], device=env.dev)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    res = dict(config=f"C3 network, {n_loc} rows/rank x {env.world} ranks, {steps} minibatches, exchange: {env.dp_mode}",
-               replicas_identical=bool(int(flag[0])))
-    if env.rank == 0:
-        dp_par = [m.means.clone() for m in net.model[:-1]] + [m.lvars.clone() for m in net.model[:-1]] + [net.model[-1].weight.clone()]
-        dp_adam = [m.get(b) for m in net.model[:-1] for b in adam_ids]
+    relf = lambda a, b: float((a.double() - b.double()).norm() / max(float(b.double().norm()), 1e-30))
+    sg_par = sg_adam = None
+    if env.rank == 0:                                                   # the single-GPU reference, once
         ctx1 = vbnn_b200.Context(env.local_rank, seed=5)                # no communicator: nranks = 1
         one, _ = build_net(w, ctx1, Ng)
         ctx1.set_step(7)
         Xg, Tg = X.cuda(), T.cuda()
         for _ in range(steps):
             one.train_step(Xg, Tg)
-        sg_par = [m.means for m in one.model[:-1]] + [m.lvars for m in one.model[:-1]] + [one.model[-1].weight]
+        sg_par = [m.means.clone() for m in one.model[:-1]] + [m.lvars.clone() for m in one.model[:-1]] + [one.model[-1].weight.clone()]
         sg_adam = [m.get(b) for m in one.model[:-1] for b in adam_ids]
-        relf = lambda a, b: float((a.double() - b.double()).norm() / max(float(b.double().norm()), 1e-30))
-        e_par = max(relf(a, b) for a, b in zip(dp_par, sg_par))
-        e_adam = max(relf(a, b) for a, b in zip(dp_adam, sg_adam))
-        t_ok = all(m.t == steps for m in net.model)
-        res.update(max_rel=max(e_par, e_adam), max_rel_params=e_par, max_rel_adam=e_adam, tol_params=1e-4, tol_adam=1e-3,
-                   step_counters_ok=t_ok)
-        res["ok"] = bool(res["replicas_identical"] and e_par < 1e-4 and e_adam < 1e-3 and t_ok)
         ctx1.synchronize()
-        del one
+        del one, Xg, Tg
         torch.cuda.set_stream(env.ctx.stream)
-    ok = torch.tensor([1 if res.get("ok", True) else 0], device=env.dev)
-    dist.broadcast(ok, 0)
-    res["ok"] = bool(int(ok[0]))
-    env.drop_net(net)
+    res = dict(config=f"C3 network, {n_loc} rows/rank x {env.world} ranks, {steps} minibatches, exchange: {env.dp_mode}",
+               tol_params=1e-4, tol_adam=1e-3, ok=True)
+    transports = [("fused", 1), ("ce", 2)] if env.dp_mode == "peer" else [(env.dp_mode, 0)]
+    for name, knob in transports:
+        old = vbnn_b200.knob("peer_transport", knob)
+        net, _ = env.make_net(w, n_loc)
+        env.ctx.set_step(7)
+        env.barrier()
+        lo = env.rank * n_loc
+        Xl, Tl = X[lo:lo + n_loc].cuda(), T[lo:lo + n_loc].cuda()
+        for _ in range(steps):
+            net.train_step(Xl, Tl)
+        env.barrier()                                                   # all streams of all ranks drained
+        net.sync_replicas()
+        env.barrier()
+        same = True
+        for m in net.model[:-1]:                                        # every rank holds identical parameters
+            t = m.means.clone(); ref = t.clone(); dist.broadcast(ref, 0)
+            same &= bool(torch.equal(ref, t))
+        flag = torch.tensor([1 if same else 0], device=env.dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        r = dict(replicas_identical=bool(int(flag[0])))
+        if env.rank == 0:
+            dp_par = [m.means for m in net.model[:-1]] + [m.lvars for m in net.model[:-1]] + [net.model[-1].weight]
+            dp_adam = [m.get(b) for m in net.model[:-1] for b in adam_ids]
+            e_par = max(relf(a, b) for a, b in zip(dp_par, sg_par))
+            e_adam = max(relf(a, b) for a, b in zip(dp_adam, sg_adam))
+            t_ok = all(m.t == steps for m in net.model)
+            r.update(max_rel_params=e_par, max_rel_adam=e_adam, step_counters_ok=t_ok,
+                     ok=bool(r["replicas_identical"] and e_par < 1e-4 and e_adam < 1e-3 and t_ok))
+        ok = torch.tensor([1 if r.get("ok", True) else 0], device=env.dev)
+        dist.broadcast(ok, 0)
+        r["ok"] = bool(int(ok[0]))
+        res[name] = r
+        res["ok"] = res["ok"] and r["ok"]
+        env.drop_net(net)
+        vbnn_b200.knob("peer_transport", old)
+    if env.rank == 0:
+        res["max_rel"] = max(max(r.get("max_rel_params", 0.0), r.get("max_rel_adam", 0.0)) for k, r in res.items() if isinstance(r, dict))
     return res
 
 

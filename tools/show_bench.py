@@ -4,7 +4,7 @@ import sys
 
 
 def show(d, ind=0):
-    for k, v in d.items():
+    for k, v in (d or {}).items():
         if isinstance(v, dict) and any(isinstance(x, dict) for x in v.values()) or k in (
                 "roofline", "roofline_hbm", "e2e", "e2e_u8", "cpu_baseline", "phases_ms_per_step", "clocks", "dp_parity"):
             print(" " * ind + k + ":")

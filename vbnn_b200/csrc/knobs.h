@@ -20,6 +20,8 @@ struct Knobs {
   int dw_split = -1;    // LRT dW as two single-accumulator GEMMs: -1 = only in peer mode
   int dp_overlap = 1;   // NCCL mode: per-layer allreduce overlapped with backward
   int no_graph = 0;     // eager launches instead of CUDA graph replay
+  int peer_transport = 0;  // gradient reduce-scatter: 0 = auto, 1 = NVLink stores from the dW epilogue, 2 = local staging + copy engines,
+                           // 3 = local staging + one co-resident copy kernel per layer (transfer + signal fused)
   int peer_fused_push = 0; // operand all-gather: 0 = copy engines (SM-free), 1 = NVLink stores from the update kernel
 };
 

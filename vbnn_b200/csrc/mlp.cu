@@ -274,13 +274,13 @@ int backward_weight_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int 
     p.ps = layer_stream(L, kStreamEps, sample0);
     p.step_ptr = m->ctx->d_step;
     if (L->eps_injected && Zrun == 1 && L->eps) p.noise = L->eps;      // parity mode: injected epsilon
-    if (scatter) peer_scatter(m, j, p);                                // reduce-scatter fused into the epilogue
+    if (scatter) peer_scatter(m, j, N, p);                             // reduce-scatter fused into the epilogue (or staged for the copy engines)
     const int mode = lrt ? EPI_DW_LRT : EPI_DW;
     // Dual dW (one launch, two accumulators, single-buffered TMEM) or two single-accumulator GEMMs
     // (double-buffered: the epilogue of tile i overlaps the MMAs of tile i+1).  On one GPU they tie; in
     // peer mode the epilogue's stores cross NVLink and the split form hides them (8 GPUs: 6.14 -> 5.97 ms).
     const int split_knob = knobs().dw_split;
-    const bool split = split_knob >= 0 ? split_knob != 0 : scatter;
+    const bool split = split_knob >= 0 ? split_knob != 0 : (scatter && !peer_transport_ce(m, N));
     if (m->bf16 && lrt && split) {
       // The two LRT parameter gradients are independent (g_mu = G^T X, g_s = H^T X^2): as two
       // single-accumulator GEMMs each tile needs half the TMEM, so the accumulator is double-buffered
@@ -352,7 +352,7 @@ int run_samples(vbnn_mlp* m, int N, int Zrun, int sample0, int accumulate, bool 
     // peer mode: layer j's operands of the previous minibatch must have landed from every owner -- waited for
     // per layer, right before they are first read, so that the exchange of the layers updated last (see the
     // backward order below) hides behind the forward GEMMs of the layers before them
-    if (peer) { VB_TRY(peer_wait_params(m, j)); VB_TRY(prof_mark(c, 1)); }
+    if (peer && !m->peer_waited_all) { VB_TRY(peer_wait_params(m, j, true)); VB_TRY(prof_mark(c, 1)); }
     VB_TRY(forward_layer(m, j, N, Zrun, sample0, false));
     VB_TRY(prof_mark(c, 3));
   }
@@ -419,8 +419,9 @@ int step_body(vbnn_mlp* m, int N) {
   if (m->peer && m->peer->active) {
     // data parallel over NVLink peer memory (peer.cu): no collective call anywhere in the step
     VB_TRY(peer_check(m));
+    m->peer_waited_all = !m->lrt;
     if (!m->lrt) {                                   // weight sampling reads mu / log sigma^2 of every layer up front
-      VB_TRY(peer_wait_params(m, -1));
+      VB_TRY(peer_wait_params(m, -1, true));
       VB_TRY(prof_mark(m->ctx, 1));
     }
     VB_TRY(sample_all(m, 0, m->Z));
@@ -783,7 +784,7 @@ extern "C" int vbnn_mlp_join_streams(vbnn_mlp* m) {
   VB_CHECK(m, VBNN_E_INVALID, "null mlp");
   vbnn_ctx* c = m->ctx;
   if (m->peer && m->peer->active) {
-    VB_CUDA(cudaEventRecord(m->peer->ev_side, m->peer->side));
+    VB_CUDA(cudaEventRecord(m->peer->ev_side, m->peer->side));     // the side stream already waits for the transfer stream
     VB_CUDA(cudaStreamWaitEvent(c->stream, m->peer->ev_side, 0));
   }
   if (c->comm_stream && !m->ev_red.empty()) {
@@ -823,7 +824,7 @@ extern "C" int vbnn_mlp_test(vbnn_mlp* m, const float* X, const float* T, int N,
   if (m->peer && m->peer->active) {
     VB_CHECK(n_samples > 0 || !m->peer->stale, VBNN_E_STATE,
              "vbnn_mlp_test(quicktest) in peer mode: call vbnn_mlp_sync_replicas on every rank first");
-    VB_TRY(peer_wait_params(m, -1));
+    VB_TRY(peer_wait_params(m, -1, false));
   }
   const int Lc = nlayers(m);
   int total = 0;

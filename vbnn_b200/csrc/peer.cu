@@ -16,7 +16,8 @@
 // Ordering uses per-layer flags in peer memory (release/acquire at system scope): grad_ready[j][r]
 // is set on every rank by rank r once its dW tile stores and gradBias of layer j are out;
 // param_ready[j][q] is set on every rank by owner q once its pushes of layer j have completed.
-// Counters are per stream (mseq: main, sseq: side), so nothing races with the host or a graph.
+// Counters are per stream (wseq: main stream's waits, mseq: the stream that signals gradients -- main or transfer --,
+// sseq: side), so nothing races with the host, a graph or another stream.
 // Every wait is bounded: a rank that does not show up sets an error word instead of hanging.
 #include <cuda.h>
 #include <string.h>
@@ -60,10 +61,15 @@ __device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t need, 
   }
 }
 
-// main stream, before the first forward GEMM of a step: every owner's operands of the previous
-// step have landed in this rank's buffers.  ready: [L][G]; seq: [2L], mseq_j = seq[2j].
-__global__ void k_wait_params(const uint32_t* ready, const uint32_t* seq, int L, int G, int* err) {
-  for (int t = threadIdx.x; t < L * G; t += blockDim.x) spin_until(ready + t, seq[2 * (t / G)], err);
+// main stream, before layer j's operands are first read in a step: every owner's operands of the previous step have
+// landed in this rank's buffers.  ready: [L][G]; wseq: [L] steps this stream has started per layer -- a counter of its
+// OWN (the gradient signal that advances mseq may run on the transfer stream, whose progress the main stream must not
+// race with); bump: training steps advance it, evaluation only looks.
+__global__ void k_wait_params(const uint32_t* ready, uint32_t* wseq, int L, int G, int* err, int bump) {
+  for (int t = threadIdx.x; t < L * G; t += blockDim.x) spin_until(ready + t, wseq[t / G], err);
+  __syncthreads();
+  if (bump)
+    for (int j = threadIdx.x; j < L; j += blockDim.x) wseq[j] += 1u;
 }
 
 struct SignalGrad {
@@ -82,6 +88,52 @@ __global__ void k_signal_grad(SignalGrad s) {
   __syncthreads();
   if (threadIdx.x < s.G) st_release_sys(s.ready_dst[threadIdx.x], v);
   if (threadIdx.x == 0) *s.mseq = v;
+}
+
+// Copy-kernel transport (strong-scaling regime): the dW GEMM left this rank's gradient tiles in a local staging copy
+// of the slot layout; this kernel -- a few small CTAs that fit beside the persistent GEMM CTAs of the next layers --
+// streams slab q to owner q over NVLink with 16-byte loads / stores (every peer link busy at once: blockIdx.x picks
+// the peer), and the last CTA of each peer also delivers gradBias and raises grad_ready there: transfer and signal in
+// ONE launch (the copy-engine form needs 2 G API calls per layer and runs the slabs one after another).
+struct PushSlabs {
+  const float* stage;              // [G][slot_floats]
+  float* dst[kMaxPeers];           // rank q's receive slot for this rank
+  size_t slot_floats;
+  const float* gb; int O;
+  float* gb_dst[kMaxPeers];
+  uint32_t* ready_dst[kMaxPeers];
+  uint32_t* mseq;
+  unsigned int* done;              // [G] CTAs finished per peer (reset by the last one)
+  int G, me;
+};
+__global__ void __launch_bounds__(128, 8) k_push_slabs(PushSlabs s) {
+  const int q = (s.me + 1 + (int)blockIdx.x) % s.G;                 // staggered start: no two ranks hit the same peer first
+  const uint4* src = reinterpret_cast<const uint4*>(s.stage + (size_t)q * s.slot_floats);
+  uint4* dst = reinterpret_cast<uint4*>(s.dst[q]);
+  const size_t n16 = s.slot_floats / 4;                             // slot_floats % 4 == 0 (rpo % 32 == 0)
+  const size_t stride = (size_t)gridDim.y * blockDim.x;
+  size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {                   // 4 x 16 B in flight per thread
+    const uint4 a = __ldcs(src + i), b = __ldcs(src + i + stride), c = __ldcs(src + i + 2 * stride), d = __ldcs(src + i + 3 * stride);
+    dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+  }
+  for (; i < n16; i += stride) dst[i] = __ldcs(src + i);
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(s.done + q, 1u) + 1u == gridDim.y;
+  __syncthreads();
+  if (!last) return;
+  for (int k = threadIdx.x; k < s.O; k += blockDim.x) s.gb_dst[q][k] = s.gb[k];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s.done[q] = 0;
+    const uint32_t v = *s.mseq + 1u;
+    st_release_sys(s.ready_dst[q], v);
+    // the counter advances once every peer has been signalled
+    if (atomicAdd(s.done + s.G, 1u) + 1u == (unsigned)s.G) { s.done[s.G] = 0; *s.mseq = v; }
+  }
 }
 
 // side stream: every rank's gradient tiles of layer j have landed in this rank's receive slots
@@ -184,26 +236,45 @@ int pull_shards(vbnn_peer* P, const PeerBuf& b, int O, size_t row_bytes, int rpo
 }  // namespace
 
 // ------------------------------------------------------------------ used by mlp.cu --------
-void peer_scatter(const vbnn_mlp* m, int j, EpiParams& p) {
+// Which way the gradient tiles travel.  Fused: the dW epilogue stores every tile straight into its owner's receive
+// slot -- no staging, no extra kernel, the transfer rides on the GEMM; right while the GEMM is compute-bound (per-rank
+// batch large: the stores need a fraction of NVLink).  With a small per-rank batch (strong scaling) the same bytes
+// must leave within a few microseconds per tile, the epilogue warps stall on posted remote stores and the tensor pipe
+// waits for its TMEM buffers (measured, C3 at 8 x 1024 rows: dW 196 TFLOP/s, 345 GB/s out of 900): there the tiles
+// are written to a LOCAL staging copy of the slot layout at full GEMM speed and the copy engines move one contiguous
+// slab per owner over NVLink while the SMs go on with the next GEMMs.
+bool peer_transport_ce(const vbnn_mlp* m, int N) {
+  const int t = knobs().peer_transport;
+  if (t == 1) return false;
+  if (t == 2 || t == 3) return true;
+  // dW compute time ~ rows; NVLink time is fixed by the parameter count: below ~4 k rows per rank the fused stores
+  // cannot hide (C3: 2 * 4096 * 4096 * rows flop per layer vs 117 MB out per layer and rank)
+  return (long long)N * m->Z < 4096;
+}
+
+void peer_scatter(const vbnn_mlp* m, int j, int N, EpiParams& p) {
   const vbnn_peer* P = m->peer;
   const PeerLayer& pl = P->layers[j];
   const vbnn_layer* L = m->layers[j];
+  const bool ce = peer_transport_ce(m, N);
   p.scatter_rows = pl.rpo;
   for (int q = 0; q < 8; ++q) { p.gW_peer[q] = nullptr; p.gS_peer[q] = nullptr; }
   for (int q = 0; q < P->G; ++q) {
-    float* slot = reinterpret_cast<float*>(P->peer_block[q] + pl.off_recv) + (size_t)P->me * pl.slot_floats;
+    float* slot = ce ? pl.stage + (size_t)q * pl.slot_floats
+                     : reinterpret_cast<float*>(P->peer_block[q] + pl.off_recv) + (size_t)P->me * pl.slot_floats;
     // pre-biased: the epilogue indexes with the GLOBAL row
     p.gW_peer[q] = slot - (long long)q * pl.rpo * L->I;
     p.gS_peer[q] = L->kind == VBNN_KIND_VB ? p.gW_peer[q] + (size_t)pl.rpo * L->I : nullptr;
   }
 }
 
-int peer_wait_params(vbnn_mlp* m, int j) {
+int peer_wait_params(vbnn_mlp* m, int j, bool bump) {
   vbnn_peer* P = m->peer;
   const int Lc = (int)m->layers.size();
   const uint32_t* ready = reinterpret_cast<const uint32_t*>(P->block + P->off_param_ready);
-  if (j < 0) k_wait_params<<<1, 256, 0, m->ctx->stream>>>(ready, P->seq, Lc, P->G, P->d_err);
-  else k_wait_params<<<1, 32, 0, m->ctx->stream>>>(ready + (size_t)j * P->G, P->seq + 2 * j, 1, P->G, P->d_err);
+  uint32_t* wseq = P->seq + 2 * Lc;
+  if (j < 0) k_wait_params<<<1, 256, 0, m->ctx->stream>>>(ready, wseq, Lc, P->G, P->d_err, bump ? 1 : 0);
+  else k_wait_params<<<1, 32, 0, m->ctx->stream>>>(ready + (size_t)j * P->G, wseq + j, 1, P->G, P->d_err, bump ? 1 : 0);
   VB_CUDA(cudaGetLastError());
   m->ctx->launches++;
   return VBNN_OK;
@@ -223,12 +294,46 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     sg.gb_dst[q] = reinterpret_cast<float*>(P->peer_block[q] + pl.off_gb) + (size_t)me * L->O;
     sg.ready_dst[q] = flag_ptr(P, q, P->off_grad_ready, j, me);
   }
-  k_signal_grad<<<1, 256, 0, c->stream>>>(sg);
-  VB_CUDA(cudaGetLastError());
-  VB_CUDA(cudaEventRecord(pl.ev_dw, c->stream));
-  // ---- side stream: wait for every rank, update this rank's rows, push, signal ----
   cudaStream_t sd = P->side;
-  VB_CUDA(cudaStreamWaitEvent(sd, pl.ev_dw, 0));
+  if (peer_transport_ce(m, m->last_N)) {
+    // copy-engine transport: one contiguous slab {gW rows, gS rows} per owner from the local staging copy, on
+    // its own stream so that the slabs of successive layers queue back to back on NVLink; the flag follows them
+    VB_CUDA(cudaEventRecord(pl.ev_dw, c->stream));
+    VB_CUDA(cudaStreamWaitEvent(P->xfer, pl.ev_dw, 0));
+    if (knobs().peer_transport == 2) {
+      // copy engines: 2 G API calls, slabs one after another
+      for (int k = 1; k <= G; ++k) {
+        const int q = (me + k) % G;                                // staggered: own shard last
+        float* dst = reinterpret_cast<float*>(P->peer_block[q] + pl.off_recv) + (size_t)me * pl.slot_floats;
+        VB_CUDA(cudaMemcpyAsync(dst, pl.stage + (size_t)q * pl.slot_floats, pl.slot_floats * 4, cudaMemcpyDefault, P->xfer));
+      }
+      k_signal_grad<<<1, 256, 0, P->xfer>>>(sg);
+    } else {
+      PushSlabs ps;
+      memset(&ps, 0, sizeof(ps));
+      ps.stage = pl.stage; ps.slot_floats = pl.slot_floats; ps.gb = L->gb; ps.O = L->O; ps.mseq = pl.mseq;
+      ps.done = P->xfer_done; ps.G = G; ps.me = me;
+      for (int q = 0; q < G; ++q) {
+        ps.dst[q] = reinterpret_cast<float*>(P->peer_block[q] + pl.off_recv) + (size_t)me * pl.slot_floats;
+        ps.gb_dst[q] = sg.gb_dst[q]; ps.ready_dst[q] = sg.ready_dst[q];
+      }
+      // ~144 small CTAs: one per SM beside the GEMM CTAs; the slab of a small layer needs fewer
+      int per_peer = (int)((pl.slot_floats / 4 + 4 * 128 - 1) / (4 * 128));
+      const int cap = kNumSMs / G > 0 ? kNumSMs / G : 1;
+      if (per_peer > cap) per_peer = cap;
+      if (per_peer < 1) per_peer = 1;
+      k_push_slabs<<<dim3(G, per_peer), 128, 0, P->xfer>>>(ps);
+    }
+    VB_CUDA(cudaGetLastError());
+    VB_CUDA(cudaEventRecord(P->ev_xfer, P->xfer));
+    VB_CUDA(cudaStreamWaitEvent(sd, P->ev_xfer, 0));
+  } else {
+    k_signal_grad<<<1, 256, 0, c->stream>>>(sg);
+    VB_CUDA(cudaGetLastError());
+    VB_CUDA(cudaEventRecord(pl.ev_dw, c->stream));
+    VB_CUDA(cudaStreamWaitEvent(sd, pl.ev_dw, 0));
+  }
+  // ---- side stream: wait for every rank, update this rank's rows, push, signal ----
   k_wait_grad<<<1, 32, 0, sd>>>(flag_ptr(P, me, P->off_grad_ready, j, 0), pl.sseq, G, P->d_err);
   VB_CUDA(cudaGetLastError());
   const float* gb_slots = reinterpret_cast<const float*>(P->block + pl.off_gb);
@@ -276,7 +381,8 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     // knob peer_fused_push: the update kernel stores the refreshed operands to every rank itself instead of
     // 2 x (G-1) copy-engine copies.  It paid when layer 0's update was the tail of the minibatch (idle SMs); with
     // the dW GEMMs issued in forward order every update runs under GEMMs, where SM-free copy engines win.
-    const bool fused_push = knobs().peer_fused_push != 0 && pl.rows > 0;
+    const bool fused_push = (knobs().peer_fused_push != 0 ||
+                             (peer_transport_ce(m, m->last_N) && knobs().peer_transport != 2)) && pl.rows > 0;
     if (fused_push) {
       for (int q = 0; q < G; ++q) {
         if (q == me) continue;
@@ -329,7 +435,11 @@ int peer_check(vbnn_mlp* m) {
 void peer_destroy(vbnn_mlp* m) {
   vbnn_peer* P = m->peer;
   if (!P) return;
+  if (P->xfer) { cudaStreamSynchronize(P->xfer); cudaStreamDestroy(P->xfer); }
   if (P->side) { cudaStreamSynchronize(P->side); cudaStreamDestroy(P->side); }
+  if (P->ev_xfer) cudaEventDestroy(P->ev_xfer);
+  if (P->xfer_done) cudaFree(P->xfer_done);
+  for (PeerLayer& pl : P->layers) if (pl.stage) cudaFree(pl.stage);
   for (void* p : P->opened) cudaIpcCloseMemHandle(p);
   for (PeerLayer& pl : P->layers) if (pl.ev_dw) cudaEventDestroy(pl.ev_dw);
   if (P->ev_side) cudaEventDestroy(P->ev_side);
@@ -379,7 +489,7 @@ extern "C" int vbnn_mlp_peer_export(vbnn_mlp* m, void* blob, size_t capacity, si
   size_t off = 0;
   P->off_grad_ready = off; off = align_up(off + (size_t)Lc * G * 4, 256);
   P->off_param_ready = off; off = align_up(off + (size_t)Lc * G * 4, 256);
-  const size_t off_seq = off; off = align_up(off + (size_t)2 * Lc * 4, 256);
+  const size_t off_seq = off; off = align_up(off + (size_t)3 * Lc * 4, 256);   // mseq, sseq per layer, then wseq[L]
   for (int j = 0; j < Lc; ++j) {
     vbnn_layer* L = m->layers[j];
     PeerLayer& pl = P->layers[j];
@@ -480,6 +590,17 @@ extern "C" int vbnn_mlp_peer_import(vbnn_mlp* m, const void* blobs, size_t blob_
   int lo = 0, hi = 0;
   VB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   VB_CUDA(cudaStreamCreateWithPriority(&P->side, cudaStreamNonBlocking, hi));
+  VB_CUDA(cudaStreamCreateWithPriority(&P->xfer, cudaStreamNonBlocking, hi));
+  VB_CUDA(cudaEventCreateWithFlags(&P->ev_xfer, cudaEventDisableTiming));
+  VB_CUDA(cudaMalloc((void**)&P->xfer_done, (kMaxPeers + 1) * sizeof(unsigned int)));
+  VB_CUDA(cudaMemsetAsync(P->xfer_done, 0, (kMaxPeers + 1) * sizeof(unsigned int), c->stream));
+  for (int j = 0; j < Lc; ++j) {
+    PeerLayer& pl = P->layers[j];
+    if (knobs().peer_transport == 1) continue;                     // fused stores only: no staging copy
+    cudaError_t e = cudaMalloc((void**)&pl.stage, (size_t)G * pl.slot_floats * 4);
+    if (e != cudaSuccess) { set_error("peer mode: cudaMalloc of the gradient staging copy failed: %s", cudaGetErrorString(e)); return VBNN_E_NOMEM; }
+    VB_CUDA(cudaMemsetAsync(pl.stage, 0, (size_t)G * pl.slot_floats * 4, c->stream));
+  }
   VB_CUDA(cudaEventCreateWithFlags(&P->ev_side, cudaEventDisableTiming));
   for (PeerLayer& pl : P->layers) VB_CUDA(cudaEventCreateWithFlags(&pl.ev_dw, cudaEventDisableTiming));
   VB_CUDA(cudaStreamSynchronize(c->stream));
@@ -498,6 +619,7 @@ extern "C" int vbnn_mlp_sync_replicas(vbnn_mlp* m) {
   vbnn_ctx* c = m->ctx;
   VB_CUDA(cudaSetDevice(c->device));
   VB_CUDA(cudaStreamSynchronize(c->stream));
+  VB_CUDA(cudaStreamSynchronize(P->xfer));
   VB_CUDA(cudaStreamSynchronize(P->side));
   VB_TRY(peer_check(m));
   for (size_t j = 0; j < m->layers.size(); ++j) {

@@ -83,6 +83,7 @@ struct PeerLayer {
   PeerBuf means, lvars, s2_f32, mu_bf16, s2_bf16, weight, w_bf16, partials, m_mu, v_mu, m_var, v_var;
   uint32_t *mseq = nullptr, *sseq = nullptr;   // step counters owned by the main / side stream
   cudaEvent_t ev_dw = nullptr;
+  float* stage = nullptr;                // copy-engine transport: local gradient tiles laid out like the G receive slots
 };
 struct vbnn_peer {
   int G = 1, me = 0;
@@ -90,9 +91,12 @@ struct vbnn_peer {
   char* peer_block[kMaxPeers] = {nullptr};
   size_t off_grad_ready = 0, off_param_ready = 0;    // uint32 [L][G] each
   std::vector<PeerLayer> layers;
-  uint32_t* seq = nullptr;                           // local counters [2 * L]
+  uint32_t* seq = nullptr;                           // local counters: {mseq, sseq} x L, then wseq[L]
   int* h_err = nullptr; int* d_err = nullptr;        // pinned + mapped: set when a peer wait times out
   cudaStream_t side = nullptr;
+  cudaStream_t xfer = nullptr;                       // copy-engine transport of gradient slabs
+  cudaEvent_t ev_xfer = nullptr;
+  unsigned int* xfer_done = nullptr;                 // copy-kernel transport: CTAs finished per peer
   cudaEvent_t ev_side = nullptr;
   std::vector<void*> opened;                         // IPC mappings to close
   bool exported = false, active = false, stale = false;
@@ -132,6 +136,7 @@ struct vbnn_mlp {
   int submit_idx = 0, collect_idx = 0, inflight = 0;
   bool pipeline_ready = false;
   int last_N = 0;
+  bool peer_waited_all = false;      // this step already waited for (and counted) every layer's operands up front
 };
 
 namespace vbnn {
@@ -145,8 +150,9 @@ PhiloxStream layer_stream(const vbnn_layer* L, uint32_t kind, int sample);
 int comm_allreduce_internal(vbnn_ctx* ctx, float* buf, size_t count, cudaStream_t st);
 // peer mode (peer.cu)
 void peer_destroy(vbnn_mlp* m);
-void peer_scatter(const vbnn_mlp* m, int j, EpiParams& p);                // dW epilogue -> owners' slots
-int peer_wait_params(vbnn_mlp* m, int j);                                 // main stream, before layer j's forward (-1: all layers)
+void peer_scatter(const vbnn_mlp* m, int j, int N, EpiParams& p);         // dW epilogue -> owners' slots (or the local staging copy of them)
+bool peer_transport_ce(const vbnn_mlp* m, int N);                         // gradient slabs travel by copy engine for this batch size
+int peer_wait_params(vbnn_mlp* m, int j, bool bump);                      // main stream, before layer j's forward (-1: all layers)
 int peer_after_dw(vbnn_mlp* m, int j);                                    // signal + owner update + push
 int peer_check(vbnn_mlp* m);                                              // host: a peer wait timed out?
 // tensor-core GEMM launch with optional event bracketing (ctx->profiling)
