@@ -500,9 +500,10 @@ def roofline_objects(m, w, N, steps, peaks, is_c3=False):
 
 def dp_parity_check(env):
     """Data-parallel vs single-GPU parity on the exact paths the scaling runs time: the C3 network (4096 wide: 256 x 256
-    CTA-pair tiles, co-resident shard updates, copy-engine operand all-gather), 1024 rows per rank, 3 minibatches, once
-    per gradient transport -- dW tiles stored into every owner's slot from the epilogue ("fused", what the weak-scaling
-    run uses) and staged locally + moved by the copy engines ("ce", what the strong-scaling run uses).  After
+    CTA-pair tiles, co-resident shard updates, operand all-gather), 1024 rows per rank, 3 minibatches, once per gradient
+    transport -- dW tiles stored into every owner's slot from the epilogue ("fused", what the weak-scaling run uses),
+    staged locally + moved by the copy engines ("copy_engine"), staged locally + moved and signalled by one co-resident
+    copy kernel per layer ("copy_kernel", what the strong-scaling run uses).  After
     sync_replicas every rank must hold -- parameters AND Adam state -- what ONE GPU stepping the whole global minibatch
     holds (identical Philox noise: zeta is indexed by the global row).  Differences are fp32 summation order only."""
     torch, dist = env.torch, env.dist
@@ -531,7 +532,7 @@ def dp_parity_check(env):
         torch.cuda.set_stream(env.ctx.stream)
     res = dict(config=f"C3 network, {n_loc} rows/rank x {env.world} ranks, {steps} minibatches, exchange: {env.dp_mode}",
                tol_params=1e-4, tol_adam=1e-3, ok=True)
-    transports = [("fused", 1), ("ce", 2)] if env.dp_mode == "peer" else [(env.dp_mode, 0)]
+    transports = [("fused", 1), ("copy_engine", 2), ("copy_kernel", 3)] if env.dp_mode == "peer" else [(env.dp_mode, 0)]
     for name, knob in transports:
         old = vbnn_b200.knob("peer_transport", knob)
         net, _ = env.make_net(w, n_loc)

@@ -284,3 +284,37 @@ def test_layer_on_legacy_default_stream_with_bound_storage():
     finally:
         lctx.close()
         torch.cuda.set_stream(old_stream)
+
+
+@pytest.mark.parametrize("force_pair", [False, True])
+@pytest.mark.parametrize("M,N,K,batch", [(100, 10, 784, 1), (300, 520, 1000, 2), (540, 600, 552, 1)])
+def test_gemm_writes_stay_in_bounds(ctx, M, N, K, batch, force_pair):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer.md), so out-of-bounds writes are looked
+    for directly: the output of the tcgen05 GEMM sits in the middle of a canary-filled allocation with a row pitch
+    wider than N; ragged tiles (TMA zero fill on the loads, predicated stores in the epilogue) must leave every
+    canary -- the guard rows above and below, and the pitch columns beside every row -- untouched."""
+    import vbnn_b200
+    from vbnn_b200 import _lib as L
+    old = [vbnn_b200.knob("tc_bn", 256 if force_pair else L.KNOB_DEFAULT), vbnn_b200.knob("tc_cg", 2 if force_pair else L.KNOB_DEFAULT)]
+    try:
+        g = torch.Generator().manual_seed(M + N + K)
+        r8 = lambda v: (v + 7) // 8 * 8
+        A = torch.randn(batch, M, K, generator=g).bfloat16(); B = torch.randn(batch, N, K, generator=g).bfloat16()
+        lda, ldb = r8(K), r8(K)
+        Ad = torch.zeros(batch, M, lda, dtype=torch.bfloat16); Ad[:, :, :K] = A
+        Bd = torch.zeros(batch, N, ldb, dtype=torch.bfloat16); Bd[:, :, :K] = B
+        Ad, Bd = Ad.cuda(), Bd.cuda()
+        ldd, guard = N + 12, 64                                           # ldd % 4 == 0 keeps the staged (coalesced) epilogue
+        CANARY = 1234.5
+        buf = torch.full((batch, M + 2 * guard, ldd), CANARY, device="cuda")
+        D = buf[:, guard:guard + M, :]
+        L.check(L.lib().vbnn_gemm_bf16(ctx.handle, C.c_void_p(Ad.data_ptr()), lda, 1, C.c_void_p(Bd.data_ptr()), ldb, 1,
+                                       C.c_void_p(D[0].data_ptr()), ldd, M, N, K, batch, M * lda, N * ldb, (M + 2 * guard) * ldd))
+        ctx.synchronize()
+        out = buf.cpu().numpy()
+        assert (out[:, :guard, :] == CANARY).all() and (out[:, guard + M:, :] == CANARY).all(), "guard rows overwritten"
+        assert (out[:, guard:guard + M, N:] == CANARY).all(), "pitch columns overwritten"
+        ref = torch.matmul(A.double(), B.double().transpose(1, 2)).numpy()
+        assert rel(out[:, guard:guard + M, :N], ref) < 1e-5
+    finally:
+        vbnn_b200.knob("tc_bn", old[0]); vbnn_b200.knob("tc_cg", old[1])

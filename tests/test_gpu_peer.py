@@ -13,16 +13,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["peer-fused", "peer-ce", "nccl"])
+@pytest.mark.parametrize("mode", ["peer-fused", "peer-ce", "peer-kernel", "nccl"])
 def test_data_parallel_matches_single_gpu(mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    # peer mode once per gradient transport: NVLink stores from the dW epilogue / local staging + copy engines
+    # peer mode once per gradient transport: NVLink stores from the dW epilogue / local staging + copy engines /
+    # local staging + the co-resident copy kernel
     env = dict(os.environ, VBNN_DP=mode.split("-")[0])
     if mode.startswith("peer-"):
-        env["VBNN_PEER_TRANSPORT"] = "1" if mode == "peer-fused" else "2"
+        env["VBNN_PEER_TRANSPORT"] = {"peer-fused": "1", "peer-ce": "2", "peer-kernel": "3"}[mode]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dp_check.py")],
                        env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)

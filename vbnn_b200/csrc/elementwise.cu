@@ -2,6 +2,8 @@
 // accesses where rows allow it, warp-shuffle + block reductions, results stay on the device.
 // Each kernel replaces a chain of THC pointwise/reduction launches in the reference; the
 // citations name the chain.
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace vbnn {
@@ -93,6 +95,18 @@ __global__ void __launch_bounds__(kThreads) k_sample_w(SampleParams p) {
         if (nv == 4) st4_bf16(dst, w[0], w[1], w[2], w[3]);
         else
           for (int j = 0; j < nv; ++j) dst[j] = __float2bfloat16_rn(w[j]);
+      }
+      if (p.eps16) {
+        __half* dst = reinterpret_cast<__half*>(p.eps16) + s * p.zs_bf16 + (long long)o * p.ld_bf16 + i0;
+        if (nv == 4) {
+          const __half2 lo = __floats2half2_rn(ep[0], ep[1]), hi = __floats2half2_rn(ep[2], ep[3]);
+          uint2 t;
+          t.x = *reinterpret_cast<const uint32_t*>(&lo);
+          t.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(dst) = t;
+        } else {
+          for (int j = 0; j < nv; ++j) dst[j] = __float2half_rn(ep[j]);
+        }
       }
     }
   }
@@ -591,6 +605,15 @@ __global__ void __launch_bounds__(kThreads) k_cast_u8(const uint8_t* src, long l
   }
 }
 
+__global__ void __launch_bounds__(kThreads) k_sum_partials(const float* __restrict__ src, int Z, long long stride, long long n,
+                                                           float scale, int accumulate, float* dst) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int z = 0; z < Z; ++z) a += src[z * stride + e];
+    dst[e] = accumulate ? dst[e] + scale * a : scale * a;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) k_square(const float* src, float* dst, long long n) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
@@ -863,6 +886,13 @@ int launch_cast_u8(const uint8_t* src, long long rows, int cols, float mean, flo
   const int ldw = dst ? ld : ld_f32;
   k_cast_u8<<<grid_for(rows * ((ldw + 7) / 8)), kThreads, 0, st>>>(src, rows, cols, mean, inv_std, dst, dst_sq, ld,
                                                                   dst_f32, dst_sq_f32, ld_f32);
+  VB_CUDA(cudaGetLastError());
+  return VBNN_OK;
+}
+
+int launch_sum_partials(const float* src, int Z, long long stride, long long n, float scale, int accumulate, float* dst,
+                        cudaStream_t st) {
+  k_sum_partials<<<grid_for(n), kThreads, 0, st>>>(src, Z, stride, n, scale, accumulate, dst);
   VB_CUDA(cudaGetLastError());
   return VBNN_OK;
 }

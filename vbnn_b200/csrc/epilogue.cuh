@@ -13,6 +13,8 @@
 //   EPI_FWD_LRT2 / EPI_DX_LRT2  the same A12 forward / backward-data maths with one of the two products
 //                read back from global memory instead of a second TMEM accumulator
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -55,6 +57,10 @@ struct EpiParams {
   int mask;                  // DX/DX_LRT: multiply by (xprev > 0)
   const float* noise;        // injected eps [M x N] (DW) / zeta [M x N] (FWD_LRT); NULL -> Philox
   long long zs_noise;
+  // DW, weight sampling on the tensor-core path: the epsilon k_sample_w drew for this minibatch, kept as fp16
+  // [Z x M x ld_e16] (2 B per weight and sample instead of regenerating Philox + Box-Muller in the epilogue, which made
+  // the multi-sample dW epilogue-bound 2:1).  One more operand rounding of the bf16 mode: |d eps| <= 2^-11 |eps|.
+  const void* eps16; int ld_e16; long long zs_e16;
   PhiloxStream ps;           // Philox stream (sample = ps.sample + z)
   const uint32_t* step_ptr;  // device step counter (overrides ps.step when non-null)
   int row0;                  // global row offset of this rank's shard (FWD_LRT zeta)
@@ -259,6 +265,10 @@ __device__ __forceinline__ void epi_quad(const EpiParams& p, const PhiloxStream&
         float e[4];
         if (p.noise) {
           load4<float>(p.noise + z * p.zs_noise + (long long)row * p.N + col, e, nvalid, (p.N & 3) == 0);
+        } else if (p.eps16) {
+          const __half* ep = reinterpret_cast<const __half*>(p.eps16) + z * p.zs_e16 + (long long)row * p.ld_e16 + col;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) e[j] = j < nvalid ? __half2float(ep[j]) : 0.f;
         } else {
           PhiloxStream ps = ps0;
           ps.sample += (uint32_t)z;

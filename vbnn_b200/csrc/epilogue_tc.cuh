@@ -72,7 +72,10 @@ __device__ __forceinline__ void stage_to_global(uint32_t stage, int lane, char* 
   for (int it = 0; it < P; ++it) {
     const int idx = it * 32 + lane, row = idx / P, pc = idx % P;
     const uint4 v = lds128(stage + stage_off<P>(row, pc));
-    if (row < rows_valid) *reinterpret_cast<uint4*>(g + row * ld_bytes + pc * 16) = v;
+    // streaming store (evict-first): epilogue outputs are not re-read by this kernel; keeping them out of the way
+    // leaves L2 to the operand tiles the CTAs in flight share (ncu r01e: dx-lrt / dw-lrt moved 1.9x their
+    // algorithmic DRAM bytes, the excess being operand tiles evicted by output write-allocates)
+    if (row < rows_valid) __stcs(reinterpret_cast<uint4*>(g + row * ld_bytes + pc * 16), v);
   }
 }
 template <int P>
@@ -81,7 +84,7 @@ __device__ __forceinline__ void global_to_stage(uint32_t stage, int lane, const 
 #pragma unroll
   for (int it = 0; it < P; ++it) {
     const int idx = it * 32 + lane, row = idx / P, pc = idx % P;
-    v[it] = row < rows_valid ? __ldg(reinterpret_cast<const uint4*>(g + row * ld_bytes + pc * 16)) : make_uint4(0, 0, 0, 0);
+    v[it] = row < rows_valid ? __ldcs(reinterpret_cast<const uint4*>(g + row * ld_bytes + pc * 16)) : make_uint4(0, 0, 0, 0);
   }
 #pragma unroll
   for (int it = 0; it < P; ++it) {
@@ -131,6 +134,7 @@ inline bool epi_can_stage(int mode, const EpiParams& p) {
   if (!ok_act(p.xprev, p.ld_x) || !ok_act(p.rprev, p.ld_x) || (p.zs_x % 8) != 0) return false;
   if (!ok_f32(p.gW, p.ld_g) || !ok_f32(p.gS, p.ld_g)) return false;
   if (!ok_f32(p.aux, p.ld_aux) || (p.zs_aux % 4) != 0) return false;
+  if (!ok_act(p.eps16, p.ld_e16) || (p.zs_e16 % 8) != 0) return false;
   if (p.scatter_rows)
     for (int q = 0; q < 8; ++q)
       if (!ok_f32(p.gW_peer[q], p.ld_g) || !ok_f32(p.gS_peer[q], p.ld_g)) return false;
@@ -260,15 +264,26 @@ __device__ __forceinline__ void epi_chunk_staged(const EpiParams& p, const Philo
         for (int j = 0; j < 32; ++j) t[j] = 0.f;
       }
       if constexpr (MODE == EPI_DW) {
-        PhiloxStream ps = ps0;
-        ps.sample += (uint32_t)z;
-        const uint32_t q = (uint32_t)((p.N + 3) >> 2);
+        if (p.eps16) {
+          uint32_t we[16];
+          get_tile_bf16(stage, lane, reinterpret_cast<const bf16*>(p.eps16) + z * p.zs_e16 + (long long)row0 * p.ld_e16 + col0,
+                        p.ld_e16, rows_valid, we);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float e[4];
-          philox_normal4(ps, (uint32_t)row * q + (uint32_t)((col0 >> 2) + j), e);
+          for (int j = 0; j < 16; ++j) {
+            const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&we[j]));
+            t[2 * j] += v1[2 * j] * e.x; t[2 * j + 1] += v1[2 * j + 1] * e.y;     // VBLinear.lua:115
+          }
+        } else {
+          PhiloxStream ps = ps0;
+          ps.sample += (uint32_t)z;
+          const uint32_t q = (uint32_t)((p.N + 3) >> 2);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) t[4 * j + k] += v1[4 * j + k] * e[k];      // VBLinear.lua:115
+          for (int j = 0; j < 8; ++j) {
+            float e[4];
+            philox_normal4(ps, (uint32_t)row * q + (uint32_t)((col0 >> 2) + j), e);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[4 * j + k] += v1[4 * j + k] * e[k];      // VBLinear.lua:115
+          }
         }
       } else {
 #pragma unroll

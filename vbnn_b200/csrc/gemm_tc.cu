@@ -136,20 +136,24 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 // CG == 2: both CTAs of the pair load into their own smem but complete the transaction on the
 // LEADER's barrier (the CTA-rank bit of the shared::cluster address is cleared).
+// L2 eviction-priority hints for TMA loads (createpolicy encodings, as in CUTLASS' CacheHintSm90)
+constexpr uint64_t kL2EvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kL2EvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
 template <int CG>
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar,
-                                            int c0, int c1, int c2) {
+                                            int c0, int c1, int c2, uint64_t hint) {
   if constexpr (CG == 1) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
         : "memory");
   } else {
     asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
         : "memory");
   }
 }
@@ -283,6 +287,7 @@ struct TcShape {
   int staged;               // every epilogue tensor is 16-byte aligned: coalesced staged I/O
   int clc;                  // dynamic scheduling: one cluster per work unit, resident clusters steal pending ones
   int zA1, zB1, zA2, zB2;   // 0: the operand is shared by every batch index z (stride 0), 1: batched
+  int hintA, hintB;         // L2 eviction priority of the A / B operand tiles: 0 normal, 1 evict-last, 2 evict-first
 };
 
 // Tile rasterisation: bands of `gm` m-tiles, inside a band n-major.  The ~#SM/CG tiles in flight
@@ -329,12 +334,12 @@ struct TcCfg {
 // One operand tile: K-major -> one {64 x ROWS} box; MN-major -> ROWS/64 boxes of {64 x BK}.
 template <int CG, bool KMAJOR, int ROWS>
 __device__ __forceinline__ void load_operand(const CUtensorMap* tm, uint32_t dst, uint32_t bar,
-                                             int mn0, int k0, int z) {
+                                             int mn0, int k0, int z, uint64_t hint) {
   if constexpr (KMAJOR) {
-    tma_load_3d<CG>(dst, tm, bar, k0, mn0, z);
+    tma_load_3d<CG>(dst, tm, bar, k0, mn0, z, hint);
   } else {
 #pragma unroll
-    for (int c = 0; c < ROWS / 64; ++c) tma_load_3d<CG>(dst + c * (BK * 128), tm, bar, mn0 + c * 64, k0, z);
+    for (int c = 0; c < ROWS / 64; ++c) tma_load_3d<CG>(dst + c * (BK * 128), tm, bar, mn0 + c * 64, k0, z, hint);
   }
 }
 
@@ -414,6 +419,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       int cs = 0; uint32_t cp = 0;          // CLC ring position as consumer
       int is = 0; uint32_t ip = 0;          // ... and as issuer (leader only)
+      const uint64_t hA = sh.hintA == 1 ? kL2EvictLast : sh.hintA == 2 ? kL2EvictFirst : kL2EvictNormal;
+      const uint64_t hB = sh.hintB == 1 ? kL2EvictLast : sh.hintB == 2 ? kL2EvictFirst : kL2EvictNormal;
       for (int w = group; w >= 0 && w < num_work; w = next_work(w, cs, cp, false)) {
         if (dyn && leader) {
           // ask for the unit after this one now, so the answer is there when the loads are out
@@ -436,11 +443,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
             if (leader) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES * CG);
             const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
             const uint32_t sb = sa + C::NACC * C::A_BYTES;
-            load_operand<CG, AK, BM>(&tmA1, sa, full_bar(stage), m0, kb * BK, z * sh.zA1);
-            load_operand<CG, BKM, C::B_ROWS>(&tmB1, sb, full_bar(stage), n0, kb * BK, z * sh.zB1);
+            load_operand<CG, AK, BM>(&tmA1, sa, full_bar(stage), m0, kb * BK, z * sh.zA1, hA);
+            load_operand<CG, BKM, C::B_ROWS>(&tmB1, sb, full_bar(stage), n0, kb * BK, z * sh.zB1, hB);
             if (DUAL) {
-              load_operand<CG, AK, BM>(&tmA2, sa + C::A_BYTES, full_bar(stage), m0, kb * BK, z * sh.zA2);
-              load_operand<CG, BKM, C::B_ROWS>(&tmB2, sb + C::B_BYTES, full_bar(stage), n0, kb * BK, z * sh.zB2);
+              load_operand<CG, AK, BM>(&tmA2, sa + C::A_BYTES, full_bar(stage), m0, kb * BK, z * sh.zA2, hA);
+              load_operand<CG, BKM, C::B_ROWS>(&tmB2, sb + C::B_BYTES, full_bar(stage), n0, kb * BK, z * sh.zB2, hB);
             }
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
@@ -554,12 +561,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = 0.f;
               }
+              if (p.eps16 && full) {
+                // epsilon as k_sample_w drew it (fp16), one coalesced 2 KB tile instead of 8 Philox + 16 Box-Muller
+                uint32_t we[16];
+                {
+                  const int ci = (c - half) / (EPIW / 4);
+                  __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float e[4];
-                philox_normal4(psz, (uint32_t)row * qn + (uint32_t)((col0 >> 2) + j), e);
+                  for (int it = 0; it < 4; ++it) {
+                    const int idx = it * 32 + lane;
+                    sts128(my_stage + stage_off<4>(idx / 4, idx % 4), pe[ci][it]);
+                  }
+                  __syncwarp();
+                  stage_get_bf16(my_stage, lane, we);
+                }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[4 * j + k] += v1[4 * j + k] * e[k];       // VBLinear.lua:115
+                for (int j = 0; j < 16; ++j) {
+                  const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&we[j]));
+                  acc[2 * j] += v1[2 * j] * e.x; acc[2 * j + 1] += v1[2 * j + 1] * e.y;   // VBLinear.lua:115
+                }
+              } else if (p.eps16) {
+                const __half* ep = reinterpret_cast<const __half*>(p.eps16) + z * p.zs_e16 + (long long)row * p.ld_e16 + col0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (row < p.M && col0 + j < p.N) acc[j] += v1[j] * __half2float(ep[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float e[4];
+                  philox_normal4(psz, (uint32_t)row * qn + (uint32_t)((col0 >> 2) + j), e);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) acc[4 * j + k] += v1[4 * j + k] * e[k];       // VBLinear.lua:115
+                }
               }
               if (last) emit(gSd, acc); else tmem_st32(tS + c * 32, acc);
             }
@@ -789,6 +822,20 @@ int launch_cfg(const TcGemmArgs& g, const EpiParams& p, cudaStream_t st) {
     if (sh.gm > sh.mt) sh.gm = sh.mt;
     sh.staged = k.tc_staged && epi_can_stage(MODE, p);
     sh.clc = k.tc_clc;
+    // L2 priorities (knob tc_l2hint, default on).  Band rasterisation keeps a band of gm m-tiles of A in flight
+    // while the n-tiles of B sweep past: the A band is what every tile of the band re-reads, so it is evict-last;
+    // B tiles are shared only by the tiles running at the same time: normal priority.  A weight operand that is
+    // small enough to stay resident for the whole kernel (B of the forward / backward-data GEMMs) is evict-last too.
+    sh.hintA = 0; sh.hintB = 0;
+    if (k.tc_l2hint == 1) {
+      const double a_band = (double)sh.gm * BM * CG * g.K * 2.0 * C::NACC;       // bytes of one A band
+      const double b_all = (double)g.N * g.K * 2.0 * C::NACC;                    // bytes of the whole B operand
+      if (b_all <= 72e6 && g.B1.zs == 0) sh.hintB = 1;
+      if (a_band <= 40e6) sh.hintA = sh.hintB == 1 && a_band + b_all > 100e6 ? 0 : 1;
+    } else if (k.tc_l2hint > 1) {              // experiments: 2 = A evict-last, 3 = B evict-last, 4 = both, 5 = A last + B first
+      sh.hintA = (k.tc_l2hint == 2 || k.tc_l2hint >= 4) ? 1 : 0;
+      sh.hintB = (k.tc_l2hint == 3 || k.tc_l2hint == 4) ? 1 : (k.tc_l2hint == 5 ? 2 : 0);
+    }
   }
   CUtensorMap tA1, tB1, tA2, tB2;
   VB_TRY(make_tmap(&tA1, g.A1, g.M, g.K, g.batch, BM));

@@ -20,6 +20,7 @@ struct SampleParams {
   float* eps_out;           // nullable [S x O x I]: keep epsilon (self.e)
   float* w_f32;             // nullable [S x O x I]
   bf16* w_bf16; int ld_bf16; long long zs_bf16;   // nullable [S x O x ld]
+  void* eps16;              // nullable [S x O x ld] (__half, same pitch / stride as w_bf16): epsilon kept for the dW epilogue
 };
 int launch_sample_w(const SampleParams& p, cudaStream_t st);
 
@@ -115,6 +116,10 @@ int launch_cast(const float* src, int src_ld, long long rows, int cols, bf16* ds
 // (+ squared copy): data.lua's normalisation (utils.lua:29-35) fused into the operand staging
 int launch_cast_u8(const uint8_t* src, long long rows, int cols, float mean, float inv_std, bf16* dst, bf16* dst_sq,
                    int ld, float* dst_f32, float* dst_sq_f32, int ld_f32, cudaStream_t st);
+// dst (+)= scale * sum_z src[z * stride + e]: fixed-order reduction of the per-sample partial products of a
+// sample-split dW GEMM (deterministic, unlike atomics)
+int launch_sum_partials(const float* src, int Z, long long stride, long long n, float scale, int accumulate, float* dst,
+                        cudaStream_t st);
 // fp32 x -> x^2 (fp32 LRT path)
 int launch_square(const float* src, float* dst, long long n, cudaStream_t st);
 // fp32 exp() (sigma^2 operand of the fp32 LRT path / bf16 copies at init)

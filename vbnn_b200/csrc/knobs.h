@@ -13,9 +13,11 @@ struct Knobs {
   int tc_cg = 0;        // force the CTA-group size (1 / 2); 0 = cost model
   int tc_gm = 0;        // raster band height in m-tiles; 0 = per-class default
   int tc_clc = 1;       // cluster launch control (dynamic tile scheduling)
+  int tc_l2hint = 0;    // L2 eviction priorities on the TMA operand loads (1: A band / resident weights evict-last; measured neutral, profiles/r02_traffic_sweep.md)
   int tc_staged = 1;    // coalesced epilogue I/O through the per-warp staging tiles
   int tc_tacc = 1;      // multi-sample dW: TMEM-resident accumulators (1: 128x128, 2: 256x128 pair)
   int tc_dw64 = 1;      // ... else the 128x64 register-accumulating form
+  int dw_eps16 = 1;     // weight sampling, bf16: keep epsilon as fp16 for the dW epilogue instead of regenerating it
   int lrt_split = 1;    // bit 0: split LRT forward, bit 1: split LRT backward-data
   int dw_split = -1;    // LRT dW as two single-accumulator GEMMs: -1 = only in peer mode
   int dp_overlap = 1;   // NCCL mode: per-layer allreduce overlapped with backward

@@ -134,6 +134,11 @@ int layer_create_internal(vbnn_ctx* ctx, int I, int O, int kind, const vbnn_opts
     if (opts->strict_reference) { A_(dev_alloc(&L->stdv, W)); A_(dev_alloc(&L->mu_sqe, W)); }
     if (!lrt && !b16) A_(dev_zalloc(&L->weight, W * L->S_alloc, st));
     if (!lrt && b16) A_(dev_zalloc(&L->w_bf16, (size_t)O * L->ldI * L->S_alloc, st));
+    if (!lrt && b16 && gW) {                       // mlp-owned: the fused minibatch keeps epsilon for the dW epilogue
+      uint16_t* e16 = nullptr;
+      A_(dev_zalloc(&e16, (size_t)O * L->ldI * L->S_alloc, st));
+      L->eps16 = e16;
+    }
     if (lrt && b16) A_(dev_zalloc(&L->mu_bf16, (size_t)O * L->ldI, st));
     if (lrt && b16) A_(dev_zalloc(&L->s2_bf16, (size_t)O * L->ldI, st));
     if (lrt && !b16) A_(dev_alloc(&L->s2_f32, W));
@@ -498,7 +503,7 @@ extern "C" int vbnn_layer_destroy(vbnn_layer* L) {
   DEV_FREE(L->m_mu); DEV_FREE(L->v_mu); DEV_FREE(L->m_var); DEV_FREE(L->v_var);
   DEV_FREE(L->eps); DEV_FREE(L->stdv); DEV_FREE(L->mu_sqe); DEV_FREE(L->s2_f32);
   DEV_FREE(L->var_hat_dev); DEV_FREE(L->t_dev); DEV_FREE(L->prior_partials);
-  DEV_FREE(L->w_bf16); DEV_FREE(L->mu_bf16); DEV_FREE(L->s2_bf16);
+  DEV_FREE(L->w_bf16); DEV_FREE(L->mu_bf16); DEV_FREE(L->s2_bf16); DEV_FREE(L->eps16);
   DEV_FREE(L->xs); DEV_FREE(L->xs2); DEV_FREE(L->gs_); DEV_FREE(L->hs); DEV_FREE(L->R);
   DEV_FREE(L->zeta_keep);
   delete L;
@@ -517,6 +522,7 @@ extern "C" int vbnn_layer_sample(vbnn_layer* L, int sample_idx, const float* eps
   L->cur_sample = sample_idx;
   L->map_mode = false;
   L->eps_injected = eps_dev != nullptr;
+  L->eps16_valid = false;
   if (is_lrt(L)) return VBNN_OK;     // local reparameterisation draws its noise in forward()
   cudaStream_t st = L->ctx->stream;
   const size_t W = (size_t)L->O * L->I;

@@ -87,10 +87,12 @@ int sample_all(vbnn_mlp* m, int sample0, int Zrun) {
     p.step_ptr = m->ctx->d_step;
     p.w_f32 = L->weight;
     p.w_bf16 = L->w_bf16; p.ld_bf16 = L->ldI; p.zs_bf16 = (long long)L->O * L->ldI;
+    p.eps16 = knobs().dw_eps16 ? L->eps16 : nullptr;
     VB_TRY(launch_sample_w(p, m->ctx->stream));
     m->ctx->launches++;
     L->map_mode = false;
     L->eps_injected = false;
+    L->eps16_valid = p.eps16 != nullptr;
   }
   return VBNN_OK;
 }
@@ -274,6 +276,9 @@ int backward_weight_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int 
     p.ps = layer_stream(L, kStreamEps, sample0);
     p.step_ptr = m->ctx->d_step;
     if (L->eps_injected && Zrun == 1 && L->eps) p.noise = L->eps;      // parity mode: injected epsilon
+    else if (L->eps16_valid && L->kind == VBNN_KIND_VB && !lrt) {      // this minibatch's epsilon, kept by sample_all
+      p.eps16 = L->eps16; p.ld_e16 = L->ldI; p.zs_e16 = (long long)L->O * L->ldI;
+    }
     if (scatter) peer_scatter(m, j, N, p);                             // reduce-scatter fused into the epilogue (or staged for the copy engines)
     const int mode = lrt ? EPI_DW_LRT : EPI_DW;
     // Dual dW (one launch, two accumulators, single-buffered TMEM) or two single-accumulator GEMMs
@@ -311,13 +316,29 @@ int backward_weight_layer(vbnn_mlp* m, int j, int N, int Zrun, int sample0, int 
         g.A2 = {(const bf16*)m->H[j], ldo, 0, zs_out};
         g.B2 = {(const bf16*)m->act2[j], ldi, 0, zs_in};
       }
-      if (L->kind == VBNN_KIND_LINEAR && Zrun > 1 && zs_in == (long long)N * ldi) {
-        // plain nn.Linear (no per-sample epsilon): sum_z G_z^T X_z is ONE GEMM over K = Z * N rows, the
-        // samples being contiguous in both operands -- no per-sample accumulator round trips
-        g.K = N * Zrun; g.batch = 1;
-        g.A1.zs = 0; g.B1.zs = 0;
+      const int lin_tiles = ceil_div(L->O, 128) * ceil_div(L->I, 128);
+      if (L->kind == VBNN_KIND_LINEAR && Zrun > 1 && !scatter && m->dw_partials && lin_tiles * 2 <= kNumSMs &&
+          (L->I & 3) == 0) {
+        // plain nn.Linear with few output tiles (the 10 x 1200 output layer of C2: 10 tiles): one tile would walk
+        // all Z * N rows serially (50 us for 0.25 GFLOP).  Instead every (tile, sample) pair is its own work unit
+        // -- a batched plain-store GEMM into per-sample partial products -- and a fixed-order reduction adds them.
+        EpiParams p0;
+        memset(&p0, 0, sizeof(p0));
+        p0.M = L->O; p0.N = L->I;
+        p0.out_f32 = m->dw_partials; p0.ld_f32 = L->I; p0.zs_f32 = (long long)L->O * L->I;
+        VB_TRY(tc_gemm(m->ctx, EPI_STORE, g, p0, EPI_DW));
+        VB_TRY(launch_sum_partials(m->dw_partials, Zrun, (long long)L->O * L->I, (long long)L->O * L->I, p.scale, accumulate,
+                                   L->gW, st));
+        m->ctx->launches++;
+      } else {
+        if (L->kind == VBNN_KIND_LINEAR && Zrun > 1 && zs_in == (long long)N * ldi) {
+          // plain nn.Linear (no per-sample epsilon): sum_z G_z^T X_z is ONE GEMM over K = Z * N rows, the
+          // samples being contiguous in both operands -- no per-sample accumulator round trips
+          g.K = N * Zrun; g.batch = 1;
+          g.A1.zs = 0; g.B1.zs = 0;
+        }
+        VB_TRY(tc_gemm(m->ctx, mode, g, p));
       }
-      VB_TRY(tc_gemm(m->ctx, mode, g, p));
     } else {
       SimtGemmArgs g;
       memset(&g, 0, sizeof(g));
@@ -551,6 +572,8 @@ extern "C" int vbnn_mlp_create(vbnn_ctx* ctx, const int* sizes, int n_sizes, int
     m->ld_aux = mx;
     A_((void**)&m->aux, ZN * (size_t)mx * 4);
   }
+  if (m->bf16 && m->Z > 1 && !vb_output)
+    A_((void**)&m->dw_partials, (size_t)m->Z * sizes[Lc - 1] * sizes[Lc] * 4);
   m->ld_logits = m->ld[Lc];
   A_((void**)&m->logits, ZN * m->ld_logits * 4);
   A_((void**)&m->targets, (size_t)max_batch * 4);
@@ -596,6 +619,7 @@ extern "C" int vbnn_mlp_destroy(vbnn_mlp* m) {
   for (void* p : m->G) if (p) cudaFree(p);
   for (void* p : m->H) if (p) cudaFree(p);
   if (m->aux) cudaFree(m->aux);
+  if (m->dw_partials) cudaFree(m->dw_partials);
   if (m->logits) cudaFree(m->logits);
   if (m->logp) cudaFree(m->logp);
   if (m->targets) cudaFree(m->targets);

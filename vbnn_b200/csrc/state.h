@@ -57,6 +57,8 @@ struct vbnn_layer {
   int* t_dev = nullptr;              // meanState.t == varState.t == biasState.evalCounter
   // bf16 tensor-core operand copies [.. x ldI]
   bf16 *w_bf16 = nullptr, *mu_bf16 = nullptr, *s2_bf16 = nullptr;
+  void* eps16 = nullptr;             // fp16 [S_alloc x O x ldI]: this minibatch's epsilon for the dW epilogue (mlp-owned layers)
+  bool eps16_valid = false;
   // layer-API scratch (grown on demand)
   int cap_N = 0;
   void *xs = nullptr, *xs2 = nullptr, *gs_ = nullptr, *hs = nullptr, *R = nullptr;
@@ -115,6 +117,7 @@ struct vbnn_mlp {
   std::vector<void*> act, act2;      // act[0] = staged input [N x ld0]; act[k>0] = [Z x N x ld_k]
   std::vector<void*> R, G, H;        // per layer output k+1: [Z x N x ld_{k+1}]
   float* aux = nullptr; int ld_aux = 0;     // fp32 [Z x N x ld_aux]: first product of the split LRT GEMMs
+  float* dw_partials = nullptr;             // fp32 [Z x O x I] of the plain output layer: per-sample dW products (Z > 1)
   float* logits = nullptr; int ld_logits = 0;
   float* logp = nullptr;
   float* targets = nullptr;          // staged targets [N]
