@@ -563,18 +563,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
               }
               if (p.eps16 && full) {
                 // epsilon as k_sample_w drew it (fp16), one coalesced 2 KB tile instead of 8 Philox + 16 Box-Muller
+                // (fetching the tile before the accumulator wait changed nothing: the kernel is bound by the L2 -> SM
+                // operand traffic of 128 x 128 tiles, not by this load)
                 uint32_t we[16];
-                {
-                  const int ci = (c - half) / (EPIW / 4);
-                  __syncwarp();
-#pragma unroll
-                  for (int it = 0; it < 4; ++it) {
-                    const int idx = it * 32 + lane;
-                    sts128(my_stage + stage_off<4>(idx / 4, idx % 4), pe[ci][it]);
-                  }
-                  __syncwarp();
-                  stage_get_bf16(my_stage, lane, we);
-                }
+                get_tile_bf16(my_stage, lane,
+                              reinterpret_cast<const bf16*>(p.eps16) + z * p.zs_e16 + (long long)row0 * p.ld_e16 + col0,
+                              p.ld_e16, rows_valid, we);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                   const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&we[j]));
