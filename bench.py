@@ -351,8 +351,8 @@ def gemm_algorithmic_bytes(cls, w, N):
     (the shape that dominates): what `traffic` (measured DRAM bytes per launch) is compared with."""
     H = w["sizes"][1]
     e = 2                                                               # bf16
-    if cls == "fwd_lrt":      # split: mean GEMM (A,B -> aux fp32) or variance GEMM (A2,B2,aux -> act, act2, R)
-        return N * H * e + H * H * e + N * H * 4                        # the lighter (mean) half; variance half adds 3 bf16 outs
+    if cls == "fwd_lrt":      # split: mean GEMM (A, B -> aux fp32) and variance GEMM (A2, B2, aux -> act, act2, R): mean of both
+        return ((N * H * e + H * H * e + N * H * 4) + (N * H * e + H * H * e + N * H * 4 + 3 * N * H * e)) // 2
     if cls == "dx_lrt":       # G, H, mu, s2 -> G_prev, H_prev (reads xprev, rprev)
         return 2 * N * H * e + 2 * H * H * e + 4 * N * H * e
     if cls == "dw_lrt":       # G, H, X, X2 -> gW, gS fp32

@@ -46,6 +46,23 @@ def main(rep, md_out, json_out, title):
     res = dict(source=md_out, gemm_launches_captured=len(gemm),
                gemm_traffic_bytes_per_launch=sum(o["dram_read"] + o["dram_write"] for o in gemm) / max(len(gemm), 1),
                per_kernel=summary)
+    # per bench.py epilogue class (what `roofline.traffic` / per_class.traffic_bytes_per_launch report), with the
+    # algorithmic bytes of the same launch for workload C3 (bench.gemm_algorithmic_bytes)
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    classes = {"fwd_lrt": ("0", "7"), "fwd": ("1",), "dx": ("3",), "dx_lrt": ("4",), "dw": ("5",), "dw_lrt": ("6",)}
+    w = bench.WORKLOADS["c3"]
+    per_class = {}
+    for cls, modes in classes.items():
+        sel = [o for o in gemm if re.match(r"gemm_tc_kernel<(\d+),", o["kernel"]).group(1) in modes]
+        if not sel:
+            continue
+        per_class[cls] = dict(dram_bytes_per_launch=sum(o["dram_read"] + o["dram_write"] for o in sel) / len(sel),
+                              algorithmic_bytes_per_launch=bench.gemm_algorithmic_bytes(cls, w, w["N"]) if cls.endswith("lrt") else None,
+                              tensor_pipe_pct=sum(o["tensor_pct"] * o["us"] for o in sel) / sum(o["us"] for o in sel),
+                              launches_captured=len(sel))
+    res["per_class"] = per_class
     json.dump(res, open(json_out, "w"), indent=1)
     with open(md_out, "w") as f:
         f.write(f"# {title}\n\n")
