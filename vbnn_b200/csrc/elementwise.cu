@@ -226,12 +226,28 @@ __global__ void __launch_bounds__(TPB, TPB == 128 ? 6 : 1) k_update(UpdateParams
       else
         for (int j = 0; j < nv; ++j) dst[e0 + j] = d[j];
     };
-    load(p.mu, mu); load(p.lvar, lv); load(p.gW, gw); load(p.gS, gs);
-    for (int src = 1; src < p.n_src; ++src) {            // peer mode: sum the ranks' receive slots
-      float a[4], b[4];
-      load(p.gW + src * p.src_stride, a); load(p.gS + src * p.src_stride, b);
+    load(p.mu, mu); load(p.lvar, lv);
+    if (p.grads_bf16) {                                  // peer mode, bf16 gradient tiles on the wire (I % 4 == 0)
+      const bf16* gWb = reinterpret_cast<const bf16*>(p.gW);
+      const bf16* gSb = reinterpret_cast<const bf16*>(p.gS);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { gw[j] += a[j]; gs[j] += b[j]; }
+      for (int j = 0; j < 4; ++j) { gw[j] = 0.f; gs[j] = 0.f; }
+      for (int src = 0; src < p.n_src; ++src) {
+        const uint2 a = *reinterpret_cast<const uint2*>(gWb + src * p.src_stride + e0);
+        const uint2 b = *reinterpret_cast<const uint2*>(gSb + src * p.src_stride + e0);
+        gw[0] += __uint_as_float(a.x << 16); gw[1] += __uint_as_float(a.x & 0xFFFF0000u);
+        gw[2] += __uint_as_float(a.y << 16); gw[3] += __uint_as_float(a.y & 0xFFFF0000u);
+        gs[0] += __uint_as_float(b.x << 16); gs[1] += __uint_as_float(b.x & 0xFFFF0000u);
+        gs[2] += __uint_as_float(b.y << 16); gs[3] += __uint_as_float(b.y & 0xFFFF0000u);
+      }
+    } else {
+      load(p.gW, gw); load(p.gS, gs);
+      for (int src = 1; src < p.n_src; ++src) {          // peer mode: sum the ranks' receive slots
+        float a[4], b[4];
+        load(p.gW + src * p.src_stride, a); load(p.gS + src * p.src_stride, b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { gw[j] += a[j]; gs[j] += b[j]; }
+      }
     }
     load(p.m_mu, mm); load(p.v_mu, vm); load(p.m_var, mv); load(p.v_var, vv);
     float sd_old[4], musq[4], s2_new[4];

@@ -72,6 +72,10 @@ struct EpiParams {
   // pre-biased so that row * ld_g + col indexes them like gW / gS); 0 = plain local gW / gS
   int scatter_rows;
   float* gW_peer[8]; float* gS_peer[8];
+  // bf16 gradient tiles (peer mode, staged transports, knob peer_wire_bf16): gW / gS (and the per-owner pointers) are bf16
+  // buffers written ONCE (accumulate == 0, one sample); halves the NVLink bytes of the reduce-scatter at the price of one
+  // more rounding point (each rank's partial sum, 2^-9 relative), stated separately in dp_parity
+  int grads_bf16;
   // split LRT modes: the other product, fp32 [M x ld_aux] (+ z * zs_aux)
   const float* aux; int ld_aux; long long zs_aux;
 };
@@ -253,6 +257,16 @@ __device__ __forceinline__ void epi_quad(const EpiParams& p, const PhiloxStream&
     const bool acc = p.accumulate || z > 0;
     float *gWd, *gSd;
     dw_dest(p, row, gWd, gSd);
+    if (p.grads_bf16) {
+      float w[4], sv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { w[j] = p.scale * a1[j]; sv[j] = MODE == EPI_DW_LRT ? a2[j] : 0.f; }
+      store4<bf16>(reinterpret_cast<bf16*>(gWd) + goff, w, nvalid, (p.ld_g & 3) == 0);
+      if (p.gS) {
+        if constexpr (MODE == EPI_DW_LRT) store4<bf16>(reinterpret_cast<bf16*>(gSd) + goff, sv, nvalid, (p.ld_g & 3) == 0);
+      }
+      return;
+    }
     float w[4] = {0.f, 0.f, 0.f, 0.f};
     if (acc) load4<float>(gWd + goff, w, nvalid, vec_g);
 #pragma unroll

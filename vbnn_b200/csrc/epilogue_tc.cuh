@@ -132,6 +132,7 @@ inline bool epi_can_stage(int mode, const EpiParams& p) {
   if (!ok_f32(p.out_f32, p.ld_f32) || (p.zs_f32 % 4) != 0) return false;
   if (!ok_act(p.out_act, p.ld_act) || !ok_act(p.out_act2, p.ld_act) || !ok_act(p.r_out, p.ld_act) || (p.zs_act % 8) != 0) return false;
   if (!ok_act(p.xprev, p.ld_x) || !ok_act(p.rprev, p.ld_x) || (p.zs_x % 8) != 0) return false;
+  if (p.grads_bf16 && (p.ld_g % 8) != 0) return false;
   if (!ok_f32(p.gW, p.ld_g) || !ok_f32(p.gS, p.ld_g)) return false;
   if (!ok_f32(p.aux, p.ld_aux) || (p.zs_aux % 4) != 0) return false;
   if (!ok_act(p.eps16, p.ld_e16) || (p.zs_e16 % 8) != 0) return false;
@@ -247,6 +248,20 @@ __device__ __forceinline__ void epi_chunk_staged(const EpiParams& p, const Philo
     const bool acc = p.accumulate || z > 0;
     float *gWd, *gSd;
     dw_dest(p, row0, gWd, gSd);
+    if (p.grads_bf16) {                                   // write-once bf16 tiles (LRT, one sample)
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = pack_bf16(p.scale * v1[2 * j], p.scale * v1[2 * j + 1]);
+      put_tile_bf16(stage, lane, reinterpret_cast<bf16*>(gWd) + goff, p.ld_g, rows_valid, w);
+      if constexpr (MODE == EPI_DW_LRT) {
+        if (p.gS) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf16(v2[2 * j], v2[2 * j + 1]);
+          put_tile_bf16(stage, lane, reinterpret_cast<bf16*>(gSd) + goff, p.ld_g, rows_valid, w);
+        }
+      }
+      return;
+    }
     float t[32];
     if (acc) {
       get_tile_f32(stage, lane, gWd + goff, p.ld_g, rows_valid, t);

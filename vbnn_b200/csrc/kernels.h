@@ -59,7 +59,8 @@ struct UpdateParams {
                                         // the compute_prior partials of the NEXT update (saves a read pass)
   // ---- peer mode (row shard of a layer; all pointers above are pre-offset to the shard, O = its rows) ----
   long long W_total;                    // weights of the WHOLE layer (var_hat denominator); 0 -> O * I
-  int n_src; long long src_stride;      // > 0: gW / gS are sums of n_src receive slots, src_stride floats apart
+  int n_src; long long src_stride;      // > 0: gW / gS are sums of n_src receive slots, src_stride ELEMENTS apart
+  int grads_bf16;                       // the slots hold bf16 tiles (gW / gS point at bf16 data; src_stride in bf16 elements)
   int grid_override;                    // > 0: blocks of this launch
   int part_off;                         // this launch's first index in the next_partials array
   int n_peer; double* peer_partials[7]; // next_partials mirrored into the other ranks' arrays (peer stores)

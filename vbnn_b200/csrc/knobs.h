@@ -24,6 +24,9 @@ struct Knobs {
   int no_graph = 0;     // eager launches instead of CUDA graph replay
   int peer_transport = 0;  // gradient reduce-scatter: 0 = auto, 1 = NVLink stores from the dW epilogue, 2 = local staging + copy engines,
                            // 3 = local staging + one co-resident copy kernel per layer (transfer + signal fused)
+  int peer_wire_bf16 = 0;  // staged transports, LRT layers: gradient tiles travel as bf16 (half the NVLink bytes; opt-in)
+  int peer_one_stream = 0; // staged transports: run the gradient transfer on the update stream (one co-resident kernel at a time)
+  int peer_push_ctas = 0;  // copy-kernel transport: CTAs per peer (0 = #SM / G)
   int peer_fused_push = 0; // operand all-gather: 0 = copy engines (SM-free), 1 = NVLink stores from the update kernel
 };
 

@@ -98,7 +98,8 @@ __global__ void k_signal_grad(SignalGrad s) {
 struct PushSlabs {
   const float* stage;              // [G][slot_floats]
   float* dst[kMaxPeers];           // rank q's receive slot for this rank
-  size_t slot_floats;
+  size_t slot_floats;              // distance between slots (floats)
+  size_t slot_bytes;               // bytes of a slot that carry data (half of it with bf16 tiles)
   const float* gb; int O;
   float* gb_dst[kMaxPeers];
   uint32_t* ready_dst[kMaxPeers];
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(128, 8) k_push_slabs(PushSlabs s) {
   const int q = (s.me + 1 + (int)blockIdx.x) % s.G;                 // staggered start: no two ranks hit the same peer first
   const uint4* src = reinterpret_cast<const uint4*>(s.stage + (size_t)q * s.slot_floats);
   uint4* dst = reinterpret_cast<uint4*>(s.dst[q]);
-  const size_t n16 = s.slot_floats / 4;                             // slot_floats % 4 == 0 (rpo % 32 == 0)
+  const size_t n16 = s.slot_bytes / 16;                             // a multiple of 16 bytes (rpo % 32 == 0)
   const size_t stride = (size_t)gridDim.y * blockDim.x;
   size_t i = (size_t)blockIdx.y * blockDim.x + threadIdx.x;
   for (; i + 3 * stride < n16; i += 4 * stride) {                   // 4 x 16 B in flight per thread
@@ -247,9 +248,16 @@ bool peer_transport_ce(const vbnn_mlp* m, int N) {
   const int t = knobs().peer_transport;
   if (t == 1) return false;
   if (t == 2 || t == 3) return true;
-  // dW compute time ~ rows; NVLink time is fixed by the parameter count: below ~4 k rows per rank the fused stores
-  // cannot hide (C3: 2 * 4096 * 4096 * rows flop per layer vs 117 MB out per layer and rank)
-  return (long long)N * m->Z < 4096;
+  // Per layer and rank the dW GEMMs take t_dw ~ 4 * rows * O * I / 1.3e15 s while 8 * O * I * (G - 1) / G bytes must leave over
+  // NVLink (t_link at ~700 GB/s): the fused stores hide while t_link < t_dw / 2, i.e. rows > 7428 * (G - 1) / G
+  // (measured: G = 2, 4096 rows: fused 3.62 ms vs staged 3.84; G = 8, 1024 rows: fused 2.74 ms vs staged 2.17)
+  const int G = m->peer ? m->peer->G : 1;
+  return (long long)N * m->Z < 7428LL * (G - 1) / G;
+}
+
+bool peer_wire_bf16(const vbnn_mlp* m, int j, int N) {
+  const vbnn_layer* L = m->layers[j];
+  return knobs().peer_wire_bf16 != 0 && peer_transport_ce(m, N) && m->bf16 && m->Z == 1 && layer_lrt(L) && (L->I & 7) == 0;
 }
 
 void peer_scatter(const vbnn_mlp* m, int j, int N, EpiParams& p) {
@@ -257,15 +265,23 @@ void peer_scatter(const vbnn_mlp* m, int j, int N, EpiParams& p) {
   const PeerLayer& pl = P->layers[j];
   const vbnn_layer* L = m->layers[j];
   const bool ce = peer_transport_ce(m, N);
+  const bool wire16 = peer_wire_bf16(m, j, N);
   p.scatter_rows = pl.rpo;
   for (int q = 0; q < 8; ++q) { p.gW_peer[q] = nullptr; p.gS_peer[q] = nullptr; }
   for (int q = 0; q < P->G; ++q) {
     float* slot = ce ? pl.stage + (size_t)q * pl.slot_floats
                      : reinterpret_cast<float*>(P->peer_block[q] + pl.off_recv) + (size_t)P->me * pl.slot_floats;
     // pre-biased: the epilogue indexes with the GLOBAL row
-    p.gW_peer[q] = slot - (long long)q * pl.rpo * L->I;
-    p.gS_peer[q] = L->kind == VBNN_KIND_VB ? p.gW_peer[q] + (size_t)pl.rpo * L->I : nullptr;
+    if (wire16) {                                        // bf16 tiles in the first half of the slot's bytes
+      bf16* s16 = reinterpret_cast<bf16*>(slot) - (long long)q * pl.rpo * L->I;
+      p.gW_peer[q] = reinterpret_cast<float*>(s16);
+      p.gS_peer[q] = reinterpret_cast<float*>(s16 + (size_t)pl.rpo * L->I);
+    } else {
+      p.gW_peer[q] = slot - (long long)q * pl.rpo * L->I;
+      p.gS_peer[q] = L->kind == VBNN_KIND_VB ? p.gW_peer[q] + (size_t)pl.rpo * L->I : nullptr;
+    }
   }
+  p.grads_bf16 = wire16 ? 1 : 0;
 }
 
 int peer_wait_params(vbnn_mlp* m, int j, bool bump) {
@@ -295,38 +311,44 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     sg.ready_dst[q] = flag_ptr(P, q, P->off_grad_ready, j, me);
   }
   cudaStream_t sd = P->side;
+  const bool wire16 = peer_wire_bf16(m, j, m->last_N);
+  const size_t slot_bytes = pl.slot_floats * (wire16 ? 2 : 4);       // bytes of a slot that carry data
   if (peer_transport_ce(m, m->last_N)) {
     // copy-engine transport: one contiguous slab {gW rows, gS rows} per owner from the local staging copy, on
     // its own stream so that the slabs of successive layers queue back to back on NVLink; the flag follows them
+    cudaStream_t xf = knobs().peer_one_stream ? sd : P->xfer;
     VB_CUDA(cudaEventRecord(pl.ev_dw, c->stream));
-    VB_CUDA(cudaStreamWaitEvent(P->xfer, pl.ev_dw, 0));
+    VB_CUDA(cudaStreamWaitEvent(xf, pl.ev_dw, 0));
     if (knobs().peer_transport == 2) {
       // copy engines: 2 G API calls, slabs one after another
       for (int k = 1; k <= G; ++k) {
         const int q = (me + k) % G;                                // staggered: own shard last
         float* dst = reinterpret_cast<float*>(P->peer_block[q] + pl.off_recv) + (size_t)me * pl.slot_floats;
-        VB_CUDA(cudaMemcpyAsync(dst, pl.stage + (size_t)q * pl.slot_floats, pl.slot_floats * 4, cudaMemcpyDefault, P->xfer));
+        VB_CUDA(cudaMemcpyAsync(dst, pl.stage + (size_t)q * pl.slot_floats, slot_bytes, cudaMemcpyDefault, xf));
       }
-      k_signal_grad<<<1, 256, 0, P->xfer>>>(sg);
+      k_signal_grad<<<1, 256, 0, xf>>>(sg);
     } else {
       PushSlabs ps;
       memset(&ps, 0, sizeof(ps));
-      ps.stage = pl.stage; ps.slot_floats = pl.slot_floats; ps.gb = L->gb; ps.O = L->O; ps.mseq = pl.mseq;
+      ps.stage = pl.stage; ps.slot_floats = pl.slot_floats; ps.slot_bytes = slot_bytes; ps.gb = L->gb; ps.O = L->O; ps.mseq = pl.mseq;
       ps.done = P->xfer_done; ps.G = G; ps.me = me;
       for (int q = 0; q < G; ++q) {
         ps.dst[q] = reinterpret_cast<float*>(P->peer_block[q] + pl.off_recv) + (size_t)me * pl.slot_floats;
         ps.gb_dst[q] = sg.gb_dst[q]; ps.ready_dst[q] = sg.ready_dst[q];
       }
       // ~144 small CTAs: one per SM beside the GEMM CTAs; the slab of a small layer needs fewer
-      int per_peer = (int)((pl.slot_floats / 4 + 4 * 128 - 1) / (4 * 128));
-      const int cap = kNumSMs / G > 0 ? kNumSMs / G : 1;
+      int per_peer = (int)((slot_bytes / 16 + 4 * 128 - 1) / (4 * 128));
+      int cap = kNumSMs / G > 0 ? kNumSMs / G : 1;
+      if (knobs().peer_push_ctas > 0) cap = knobs().peer_push_ctas;
       if (per_peer > cap) per_peer = cap;
       if (per_peer < 1) per_peer = 1;
-      k_push_slabs<<<dim3(G, per_peer), 128, 0, P->xfer>>>(ps);
+      k_push_slabs<<<dim3(G, per_peer), 128, 0, xf>>>(ps);
     }
     VB_CUDA(cudaGetLastError());
-    VB_CUDA(cudaEventRecord(P->ev_xfer, P->xfer));
-    VB_CUDA(cudaStreamWaitEvent(sd, P->ev_xfer, 0));
+    if (xf != sd) {
+      VB_CUDA(cudaEventRecord(P->ev_xfer, xf));
+      VB_CUDA(cudaStreamWaitEvent(sd, P->ev_xfer, 0));
+    }
   } else {
     k_signal_grad<<<1, 256, 0, c->stream>>>(sg);
     VB_CUDA(cudaGetLastError());
@@ -357,6 +379,11 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     u.mu = L->means + roff; u.lvar = L->lvars + roff;
     u.gW = slot0; u.gS = slot0 + (size_t)pl.rpo * L->I;
     u.n_src = G; u.src_stride = (long long)pl.slot_floats;
+    if (wire16) {                                        // bf16 tiles: gS follows gW inside the first half of each slot
+      u.grads_bf16 = 1;
+      u.gS = reinterpret_cast<const float*>(reinterpret_cast<const bf16*>(slot0) + (size_t)pl.rpo * L->I);
+      u.src_stride = (long long)pl.slot_floats * 2;
+    }
     u.m_mu = L->m_mu + roff; u.v_mu = L->v_mu + roff; u.m_var = L->m_var + roff; u.v_var = L->v_var + roff;
     u.mu_bf16 = L->mu_bf16 ? L->mu_bf16 + roffb : nullptr;
     u.s2_bf16 = L->s2_bf16 ? L->s2_bf16 + roffb : nullptr;
@@ -381,8 +408,9 @@ int peer_after_dw(vbnn_mlp* m, int j) {
     // knob peer_fused_push: the update kernel stores the refreshed operands to every rank itself instead of
     // 2 x (G-1) copy-engine copies.  It paid when layer 0's update was the tail of the minibatch (idle SMs); with
     // the dW GEMMs issued in forward order every update runs under GEMMs, where SM-free copy engines win.
-    const bool fused_push = (knobs().peer_fused_push != 0 ||
-                             (peer_transport_ce(m, m->last_N) && knobs().peer_transport != 2)) && pl.rows > 0;
+    const int fp_knob = knobs().peer_fused_push;         // 1: always, -1: never, 0: with the copy-kernel transport
+    const bool fused_push = (fp_knob > 0 || (fp_knob == 0 && peer_transport_ce(m, m->last_N) && knobs().peer_transport != 2)) &&
+                            pl.rows > 0;
     if (fused_push) {
       for (int q = 0; q < G; ++q) {
         if (q == me) continue;

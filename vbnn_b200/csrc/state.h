@@ -154,7 +154,8 @@ int comm_allreduce_internal(vbnn_ctx* ctx, float* buf, size_t count, cudaStream_
 // peer mode (peer.cu)
 void peer_destroy(vbnn_mlp* m);
 void peer_scatter(const vbnn_mlp* m, int j, int N, EpiParams& p);         // dW epilogue -> owners' slots (or the local staging copy of them)
-bool peer_transport_ce(const vbnn_mlp* m, int N);                         // gradient slabs travel by copy engine for this batch size
+bool peer_transport_ce(const vbnn_mlp* m, int N);
+bool peer_wire_bf16(const vbnn_mlp* m, int j, int N);                     // layer j's gradient tiles travel as bf16 for this batch size                         // gradient slabs travel by copy engine for this batch size
 int peer_wait_params(vbnn_mlp* m, int j, bool bump);                      // main stream, before layer j's forward (-1: all layers)
 int peer_after_dw(vbnn_mlp* m, int j);                                    // signal + owner update + push
 int peer_check(vbnn_mlp* m);                                              // host: a peer wait timed out?
