@@ -81,3 +81,36 @@ def test_lua_shim_binds_only_exported_symbols():
         src = open(os.path.join(root, "lua", fn)).read()
         for name in set(re.findall(r"\bC\.(vbnn_[a-z0-9_]+)", src)):
             assert name in declared, (fn, name)
+
+
+def test_debug_knobs_and_ctx_create_ex_argument_checks():
+    """(no GPU needed) vbnn_debug_knob round trip, unknown names, and the argument validation of
+    vbnn_ctx_create_ex that precedes any CUDA call."""
+    from vbnn_b200 import _lib
+    lib = _lib.lib()
+    old = _lib.knob("tc_bn", 256)
+    assert _lib.knob("tc_bn", old) == 256                                # returns the previous value
+    assert _lib.knob("tc_bn") == old and _lib.knob("tc_bn") == old       # KNOB_DEFAULT restores env / default
+    with pytest.raises(_lib.VbnnError) as e:
+        _lib.knob("no_such_knob", 1)
+    assert e.value.code == _lib.E_INVALID
+    h = C.c_void_p()
+    assert lib.vbnn_ctx_create_ex(0, None, 7, 3, C.byref(h)) == _lib.E_INVALID          # bad stream mode
+    fake = C.c_void_p(0x10)
+    assert lib.vbnn_ctx_create_ex(0, fake, _lib.STREAM_LEGACY_DEFAULT, 3, C.byref(h)) == _lib.E_INVALID   # stream must be NULL
+    assert b"stream must be NULL" in lib.vbnn_last_error()
+
+
+def test_peer_shard_layout():
+    """(no GPU needed) rows per owner are a multiple of 32, shards tile [0, O) without overlap, trailing ranks may be empty."""
+    from vbnn_b200 import _lib
+    lib = _lib.lib()
+    for O, G in [(4096, 8), (1000, 8), (100, 8), (10, 2), (1200, 3), (33, 4)]:
+        r0, rows = C.c_int(), C.c_int()
+        covered = 0
+        for q in range(G):
+            rpo = lib.vbnn_peer_shard(O, G, q, C.byref(r0), C.byref(rows))
+            assert rpo % 32 == 0 and rpo * G >= O
+            assert r0.value == min(q * rpo, O) and 0 <= rows.value <= rpo
+            covered += rows.value
+        assert covered == O

@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 
 #include "kernels.h"
+#include "knobs.h"
 
 namespace vbnn {
 
@@ -749,7 +750,7 @@ int launch_prior_partials(const float* mu, const float* lvar, long long n, doubl
 
 int update_grid(int O, int I) {
   const long long quads = (long long)O * ((I + 3) / 4);
-  int grid = grid_for(quads, 4);
+  int grid = grid_for(quads, knobs().upd_bps > 0 ? knobs().upd_bps : 4);
   return grid > kMaxPartials ? kMaxPartials : grid;
 }
 

@@ -16,7 +16,7 @@ const Entry kTable[] = {
     {"tc_bn", &Knobs::tc_bn},           {"tc_cg", &Knobs::tc_cg},         {"tc_gm", &Knobs::tc_gm},
     {"tc_clc", &Knobs::tc_clc},         {"tc_l2hint", &Knobs::tc_l2hint},         {"tc_staged", &Knobs::tc_staged}, {"tc_tacc", &Knobs::tc_tacc},
     {"tc_dw64", &Knobs::tc_dw64},       {"dw_eps16", &Knobs::dw_eps16},       {"lrt_split", &Knobs::lrt_split}, {"dw_split", &Knobs::dw_split},
-    {"dp_overlap", &Knobs::dp_overlap}, {"no_graph", &Knobs::no_graph},   {"peer_fused_push", &Knobs::peer_fused_push}, {"peer_transport", &Knobs::peer_transport}, {"peer_one_stream", &Knobs::peer_one_stream},
+    {"dp_overlap", &Knobs::dp_overlap}, {"no_graph", &Knobs::no_graph},   {"upd_bps", &Knobs::upd_bps},   {"peer_fused_push", &Knobs::peer_fused_push}, {"peer_transport", &Knobs::peer_transport}, {"peer_one_stream", &Knobs::peer_one_stream},
     {"peer_push_ctas", &Knobs::peer_push_ctas}, {"peer_wire_bf16", &Knobs::peer_wire_bf16},
 };
 
