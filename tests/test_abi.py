@@ -99,18 +99,3 @@ def test_debug_knobs_and_ctx_create_ex_argument_checks():
     fake = C.c_void_p(0x10)
     assert lib.vbnn_ctx_create_ex(0, fake, _lib.STREAM_LEGACY_DEFAULT, 3, C.byref(h)) == _lib.E_INVALID   # stream must be NULL
     assert b"stream must be NULL" in lib.vbnn_last_error()
-
-
-def test_peer_shard_layout():
-    """(no GPU needed) rows per owner are a multiple of 32, shards tile [0, O) without overlap, trailing ranks may be empty."""
-    from vbnn_b200 import _lib
-    lib = _lib.lib()
-    for O, G in [(4096, 8), (1000, 8), (100, 8), (10, 2), (1200, 3), (33, 4)]:
-        r0, rows = C.c_int(), C.c_int()
-        covered = 0
-        for q in range(G):
-            rpo = lib.vbnn_peer_shard(O, G, q, C.byref(r0), C.byref(rows))
-            assert rpo % 32 == 0 and rpo * G >= O
-            assert r0.value == min(q * rpo, O) and 0 <= rows.value <= rpo
-            covered += rows.value
-        assert covered == O

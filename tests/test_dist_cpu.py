@@ -116,7 +116,7 @@ def test_peer_shard_layout():
         assert len(rpos) == 1
 
 
-def _peer_worker(rank, world, port, ret):
+def _peer_worker(rank, world, port, ret, wire_bf16=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -135,6 +135,8 @@ def _peer_worker(rank, world, port, ret):
         slots = {}
         for name in ("gradWeight", "gradSum", "gradBias"):
             mine = getattr(lyr, name).clone()
+            if wire_bf16 and name != "gradBias":
+                mine = O.round_bf16(mine)                           # knob peer_wire_bf16: each rank's tile is rounded once
             allr = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(allr, mine)
             slots[name] = allr
@@ -161,8 +163,12 @@ def _peer_worker(rank, world, port, ret):
         lyr.update(opt)
     err = 0.0
     for a, b in zip(net.vb, ref.vb):
-        err = max(err, float((a.means - b.means).abs().max()), float((a.lvars - b.lvars).abs().max()),
-                  float((a.bias - b.bias).abs().max()))
+        if wire_bf16:     # relative Frobenius error: a rounded partial flips the sign of a near-zero gradient now and then,
+            err = max(err, float((a.means - b.means).norm() / b.means.norm()),          # and Adam's first step is +-lr
+                      float((a.lvars - b.lvars).norm() / b.lvars.norm()), float((a.bias - b.bias).abs().max()))
+        else:
+            err = max(err, float((a.means - b.means).abs().max()), float((a.lvars - b.lvars).abs().max()),
+                      float((a.bias - b.bias).abs().max()))
     ret[rank] = err
     dist.destroy_process_group()
 
@@ -175,3 +181,17 @@ def test_peer_reduce_scatter_sharded_update_allgather_equals_single():
     assert len(ret) == world
     for r in range(world):
         assert ret[r] < 1e-12, ret[r]
+
+
+def test_peer_exchange_with_bf16_tiles_on_the_wire_is_bounded():
+    """knob peer_wire_bf16 (opt-in, strong-scaling regime): every rank's gradient tile is rounded to bf16 once before the
+    owner sums the slots in fp32.  Same exchange algebra; the parameters after the update stay within the bound bench.py's
+    dp_parity states for that mode (relative Frobenius error <= 1e-3), and all ranks still agree exactly."""
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_peer_worker, args=(world, port, ret, True), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        assert 0.0 < ret[r] < 1e-3, ret[r]
+    assert ret[0] == ret[1]
