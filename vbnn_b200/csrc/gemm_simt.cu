@@ -13,6 +13,8 @@
 namespace vbnn {
 
 constexpr int TM = 64, TN = 64, TK = 16;
+__device__ __forceinline__ int ceil_div_dev(int a, int b) { return (a + b - 1) / b; }
+__device__ __forceinline__ int round_up_dev(int a, int b) { return (a + b - 1) / b * b; }
 
 template <bool DUAL>
 struct SimtSmem {
@@ -44,24 +46,30 @@ __device__ __forceinline__ void load_tile(float (*dst)[TM + 4], const float* __r
   }
 }
 
+// ksplit > 1: blockIdx.z = z * ksplit + ks and CTA ks contracts only its slice of K, leaving raw partial accumulators in
+// `scratch` [(z * ksplit + ks) * NACC + a][M x N]; k_simt_finish then adds the slices in a fixed order and runs the fused
+// epilogue.  For the tiny launch-bound configs (C1: 100 x 100 outputs, K = 784 -- 4 CTAs walking 49 k-steps serially)
+// this turns one long dependent chain into ksplit short ones.
 template <int MODE, bool DUAL>
-__global__ void __launch_bounds__(256) gemm_simt_kernel(SimtGemmArgs g, EpiParams p) {
+__global__ void __launch_bounds__(256) gemm_simt_kernel(SimtGemmArgs g, EpiParams p, int ksplit, float* scratch) {
   __shared__ SimtSmem<DUAL> sm;
-  const int z = blockIdx.z;
+  const int z = blockIdx.z / ksplit, ks = blockIdx.z - z * ksplit;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const float* A1 = g.A1 + z * g.zsA1;
   const float* B1 = g.B1 + z * g.zsB1;
   const float* A2 = DUAL ? g.A2 + z * g.zsA2 : nullptr;
   const float* B2 = DUAL ? g.B2 + z * g.zsB2 : nullptr;
+  const int kchunk = ksplit > 1 ? round_up_dev(ceil_div_dev(g.K, ksplit), TK) : g.K;
+  const int k_begin = ks * kchunk, k_end = min(g.K, k_begin + kchunk);
 
   float acc1[4][4] = {}, acc2[4][4] = {};
-  for (int k0 = 0; k0 < g.K; k0 += TK) {
-    load_tile(sm.a[0], A1, g.sA1m, g.sA1k, m0, k0, g.M, g.K);
-    load_tile(sm.b[0], B1, g.sB1n, g.sB1k, n0, k0, g.N, g.K);
+  for (int k0 = k_begin; k0 < k_end; k0 += TK) {
+    load_tile(sm.a[0], A1, g.sA1m, g.sA1k, m0, k0, g.M, k_end);
+    load_tile(sm.b[0], B1, g.sB1n, g.sB1k, n0, k0, g.N, k_end);
     if (DUAL) {
-      load_tile(sm.a[DUAL ? 1 : 0], A2, g.sA2m, g.sA2k, m0, k0, g.M, g.K);
-      load_tile(sm.b[DUAL ? 1 : 0], B2, g.sB2n, g.sB2k, n0, k0, g.N, g.K);
+      load_tile(sm.a[DUAL ? 1 : 0], A2, g.sA2m, g.sA2k, m0, k0, g.M, k_end);
+      load_tile(sm.b[DUAL ? 1 : 0], B2, g.sB2n, g.sB2k, n0, k0, g.N, k_end);
     }
     __syncthreads();
 #pragma unroll
@@ -85,9 +93,93 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(SimtGemmArgs g, EpiParam
     }
     __syncthreads();
   }
+  if (ksplit > 1) {
+    constexpr int NACC = DUAL ? 2 : 1;
+    const long long MN = (long long)g.M * g.N;
+    float* s1 = scratch + ((long long)blockIdx.z * NACC) * MN;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = m0 + ty * 4 + i;
+      if (row >= g.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = n0 + tx * 4 + j;
+        if (col >= g.N) continue;
+        s1[(long long)row * g.N + col] = acc1[i][j];
+        if (DUAL) s1[MN + (long long)row * g.N + col] = acc2[i][j];
+      }
+    }
+    return;
+  }
   const PhiloxStream ps = epi_stream(p);
 #pragma unroll
   for (int i = 0; i < 4; ++i) epi_quad<MODE, float>(p, ps, z, m0 + ty * 4 + i, n0 + tx * 4, acc1[i], acc2[i]);
+}
+
+// one thread per quad: add the K slices in slice order, then the same fused epilogue
+template <int MODE, bool DUAL>
+__global__ void __launch_bounds__(256) k_simt_finish(int M, int N, int batch, int ksplit, const float* scratch, EpiParams p) {
+  constexpr int NACC = DUAL ? 2 : 1;
+  const int Q = (N + 3) >> 2;
+  const long long quads = (long long)batch * M * Q, MN = (long long)M * N;
+  const PhiloxStream ps = epi_stream(p);
+  for (long long qd = blockIdx.x * (long long)blockDim.x + threadIdx.x; qd < quads; qd += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(qd / ((long long)M * Q));
+    const long long r = qd - (long long)z * M * Q;
+    const int row = (int)(r / Q), col = (int)(r - (long long)row * Q) * 4;
+    float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ks = 0; ks < ksplit; ++ks) {
+      const float* s1 = scratch + ((long long)(z * ksplit + ks) * NACC) * MN + (long long)row * N + col;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (col + j < N) { a1[j] += s1[j]; if (DUAL) a2[j] += s1[MN + j]; }
+    }
+    epi_quad<MODE, float>(p, ps, z, row, col, a1, a2);
+  }
+}
+
+// scratch for the K-split partials, grown on demand (first use of a shape happens in the eager first minibatch, before
+// any graph capture)
+static float* g_scratch = nullptr;
+static size_t g_scratch_floats = 0;
+static int ensure_scratch(size_t floats) {
+  if (floats <= g_scratch_floats) return VBNN_OK;
+  VB_CUDA(cudaDeviceSynchronize());
+  if (g_scratch) cudaFree(g_scratch);
+  g_scratch = nullptr; g_scratch_floats = 0;
+  VB_CUDA(cudaMalloc((void**)&g_scratch, floats * sizeof(float)));
+  g_scratch_floats = floats;
+  return VBNN_OK;
+}
+
+static int choose_ksplit(const SimtGemmArgs& g, int batch) {
+  const long long ctas = (long long)ceil_div(g.N, TN) * ceil_div(g.M, TM) * batch;
+  if (ctas > 32 || g.K < 256) return 1;
+  int ks = g.K / 128;
+  return ks < 1 ? 1 : (ks > 8 ? 8 : ks);
+}
+
+template <int MODE>
+static int launch_one(const SimtGemmArgs& g, const EpiParams& p, int batch, cudaStream_t st) {
+  constexpr bool DUAL = epi_is_dual(MODE);
+  int ksplit = choose_ksplit(g, batch);
+  if (ksplit > 1) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    const size_t need = (size_t)batch * ksplit * (DUAL ? 2 : 1) * g.M * g.N;
+    if (need > g_scratch_floats && cs != cudaStreamCaptureStatusNone) ksplit = 1;     // never allocate inside a capture
+    else VB_TRY(ensure_scratch(need));
+  }
+  dim3 grid(ceil_div(g.N, TN), ceil_div(g.M, TM), batch * ksplit);
+  gemm_simt_kernel<MODE, DUAL><<<grid, 256, 0, st>>>(g, p, ksplit, g_scratch);
+  if (ksplit > 1) {
+    const long long quads = (long long)batch * g.M * ((g.N + 3) / 4);
+    int blocks = (int)((quads + 255) / 256);
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    k_simt_finish<MODE, DUAL><<<blocks, 256, 0, st>>>(g.M, g.N, batch, ksplit, g_scratch, p);
+  }
+  VB_CUDA(cudaGetLastError());
+  return VBNN_OK;
 }
 
 template <int MODE>
@@ -103,21 +195,21 @@ static int launch_mode(const SimtGemmArgs& g, const EpiParams& p, int batch, cud
       EpiParams pz = p;
       pz.ps.sample += z;
       if (pz.noise) pz.noise += z * p.zs_noise;
+      if (pz.eps16) pz.eps16 = reinterpret_cast<const char*>(pz.eps16) + (long long)z * p.zs_e16 * 2;
       pz.accumulate = p.accumulate || z > 0;
-      dim3 grid(ceil_div(g.N, TN), ceil_div(g.M, TM), 1);
-      gemm_simt_kernel<MODE, DUAL><<<grid, 256, 0, st>>>(gz, pz);
+      VB_TRY(launch_one<MODE>(gz, pz, 1, st));
     }
-  } else {
-    dim3 grid(ceil_div(g.N, TN), ceil_div(g.M, TM), batch);
-    gemm_simt_kernel<MODE, DUAL><<<grid, 256, 0, st>>>(g, p);
+    return VBNN_OK;
   }
-  VB_CUDA(cudaGetLastError());
-  return VBNN_OK;
+  return launch_one<MODE>(g, p, batch, st);
 }
 
 int gemm_simt_launch(int mode, const SimtGemmArgs& g, const EpiParams& p, int batch,
                      cudaStream_t st, long long* launches) {
-  if (launches) *launches += epi_z_accumulates(mode) ? batch : 1;
+  if (launches) {
+    const bool zacc = epi_z_accumulates(mode);
+    *launches += (long long)(zacc ? batch : 1) * (choose_ksplit(g, zacc ? 1 : batch) > 1 ? 2 : 1);   // + the K-split finish kernel
+  }
   switch (mode) {
     case EPI_STORE: return launch_mode<EPI_STORE>(g, p, batch, st);
     case EPI_FWD: return launch_mode<EPI_FWD>(g, p, batch, st);
