@@ -8,6 +8,9 @@
 //   forward   Y  = X W^T      (A = X [N x I], B(k,n) = W[n*ldw + k])          nn.Linear:updateOutput
 //   backward  dX = G W        (A = G [N x O], B(k,n) = W[k*ldw + n])          nn.Linear:updateGradInput
 //   wgrad     dW = G^T X      (A(m,k) = G[k*ldg + m], B(k,n) = X[k*ldx + n])  VBLinear.lua:113-115
+#include <map>
+#include <utility>
+
 #include "gemm.h"
 
 namespace vbnn {
@@ -138,17 +141,22 @@ __global__ void __launch_bounds__(256) k_simt_finish(int M, int N, int batch, in
   }
 }
 
-// scratch for the K-split partials, grown on demand (first use of a shape happens in the eager first minibatch, before
-// any graph capture)
-static float* g_scratch = nullptr;
-static size_t g_scratch_floats = 0;
-static int ensure_scratch(size_t floats) {
-  if (floats <= g_scratch_floats) return VBNN_OK;
-  VB_CUDA(cudaDeviceSynchronize());
-  if (g_scratch) cudaFree(g_scratch);
-  g_scratch = nullptr; g_scratch_floats = 0;
-  VB_CUDA(cudaMalloc((void**)&g_scratch, floats * sizeof(float)));
-  g_scratch_floats = floats;
+// Scratch for the K-split partials: one fixed-size buffer per (device, stream), allocated on first use and never moved
+// (a captured CUDA graph bakes the pointer into its kernel nodes).  The heuristic below bounds the need:
+// <= 32 CTAs x 64 x 64 outputs x 8 slices x 2 accumulators.
+constexpr size_t kScratchFloats = (size_t)32 * TM * TN * 8 * 2;
+static std::map<std::pair<int, cudaStream_t>, float*> g_scratch;
+static int get_scratch(cudaStream_t st, bool may_allocate, float** out) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = g_scratch.find({dev, st});
+  if (it != g_scratch.end()) { *out = it->second; return VBNN_OK; }
+  *out = nullptr;
+  if (!may_allocate) return VBNN_OK;
+  float* p = nullptr;
+  VB_CUDA(cudaMalloc((void**)&p, kScratchFloats * sizeof(float)));
+  g_scratch[{dev, st}] = p;
+  *out = p;
   return VBNN_OK;
 }
 
@@ -163,20 +171,21 @@ template <int MODE>
 static int launch_one(const SimtGemmArgs& g, const EpiParams& p, int batch, cudaStream_t st) {
   constexpr bool DUAL = epi_is_dual(MODE);
   int ksplit = choose_ksplit(g, batch);
+  float* scratch = nullptr;
   if (ksplit > 1) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);
+    VB_TRY(get_scratch(st, cs == cudaStreamCaptureStatusNone, &scratch));      // never allocate inside a capture
     const size_t need = (size_t)batch * ksplit * (DUAL ? 2 : 1) * g.M * g.N;
-    if (need > g_scratch_floats && cs != cudaStreamCaptureStatusNone) ksplit = 1;     // never allocate inside a capture
-    else VB_TRY(ensure_scratch(need));
+    if (!scratch || need > kScratchFloats) ksplit = 1;
   }
   dim3 grid(ceil_div(g.N, TN), ceil_div(g.M, TM), batch * ksplit);
-  gemm_simt_kernel<MODE, DUAL><<<grid, 256, 0, st>>>(g, p, ksplit, g_scratch);
+  gemm_simt_kernel<MODE, DUAL><<<grid, 256, 0, st>>>(g, p, ksplit, scratch);
   if (ksplit > 1) {
     const long long quads = (long long)batch * g.M * ((g.N + 3) / 4);
     int blocks = (int)((quads + 255) / 256);
     if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-    k_simt_finish<MODE, DUAL><<<blocks, 256, 0, st>>>(g.M, g.N, batch, ksplit, g_scratch, p);
+    k_simt_finish<MODE, DUAL><<<blocks, 256, 0, st>>>(g.M, g.N, batch, ksplit, scratch, p);
   }
   VB_CUDA(cudaGetLastError());
   return VBNN_OK;
