@@ -32,6 +32,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ uint32_t bf16x2_square(uint32_t w) {
+  const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(&w);
+  const __nv_bfloat162 r = __hmul2(t, t);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
@@ -204,9 +209,10 @@ __device__ __forceinline__ void epi_chunk_staged(const EpiParams& p, const Philo
       }
       wa[2 * j] = pack_bf16(ya[0], ya[1]); wa[2 * j + 1] = pack_bf16(ya[2], ya[3]);
       wr[2 * j] = pack_bf16(rr[0], rr[1]); wr[2 * j + 1] = pack_bf16(rr[2], rr[3]);
-      // square the value the next layer will actually read (the bf16-rounded activation)
-      const float a0 = bf16_lo(wa[2 * j]), a1 = bf16_hi(wa[2 * j]), a2 = bf16_lo(wa[2 * j + 1]), a3 = bf16_hi(wa[2 * j + 1]);
-      w2[2 * j] = pack_bf16(a0 * a0, a1 * a1); w2[2 * j + 1] = pack_bf16(a2 * a2, a3 * a3);
+      // square the value the next layer will actually read (the bf16-rounded activation): one packed bf16 multiply
+      // per pair -- the exact product of two bf16 fits fp32, so rounding it once to bf16 (HMUL2.BF16) equals the
+      // unpack / FMUL / pack sequence bit for bit
+      w2[2 * j] = bf16x2_square(wa[2 * j]); w2[2 * j + 1] = bf16x2_square(wa[2 * j + 1]);
     }
     const long long off = z * p.zs_act + (long long)row0 * p.ld_act + col0;
     if (p.out_f32)
