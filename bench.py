@@ -27,7 +27,6 @@ Prints ONE JSON line (rank 0):
 The oracle is only ever the checker / CPU baseline, never the product."""
 import argparse
 import json
-import math
 import os
 import statistics
 import subprocess
@@ -366,7 +365,7 @@ def gemm_algorithmic_bytes(cls, w, N):
     return None
 
 
-def measure(env, args, w, N, steps, warmup, sampler=None, e2e=True, tag=""):
+def measure(env, args, w, N, steps, warmup, sampler=None, e2e=True):
     """Time `steps` minibatches of workload w at N rows per GPU.  Returns the measurement dict."""
     torch = env.torch
     world, rank, ctx = env.world, env.rank, env.ctx

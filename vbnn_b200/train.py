@@ -3,7 +3,6 @@ resident on the device: minibatch assembly (data.lua:9-20) is a device gather by
 vector (utils.lua:90-94), there is no per-batch :cuda() copy and no collectgarbage()."""
 from __future__ import annotations
 
-import math
 
 
 def synthetic_dataset(n, input_size, n_classes, seed=3, device="cuda", geometry=None):
