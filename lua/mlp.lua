@@ -22,7 +22,7 @@ function MLP:buildModel(opt)                                          -- referen
    local csizes = ffi.new('int[?]', #sizes, sizes)
    local out = ffi.new('vbnn_mlp*[1]')
    -- hidden layers: VBLinear + ReLU; output: plain nn.Linear + LogSoftMax (mlp.lua:29-30)
-   V.check(C.vbnn_mlp_create(V.context(opt.seed), csizes, #sizes, 0, opt.batchSize, V.opts(opt), out))
+   V.check(C.vbnn_mlp_create(V.context(opt.seed, true), csizes, #sizes, 0, opt.batchSize, V.opts(opt), out))
    net.h = ffi.gc(out[0], C.vbnn_mlp_destroy)
    V.check(C.vbnn_mlp_init_params(net.h, opt.param_seed or 4, opt.msr_init and 1 or 0))     -- mlp.lua:47-55
    net.s = 0

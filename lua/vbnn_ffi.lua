@@ -66,7 +66,7 @@ function M.check(rc)
 end
 
 -- stream modes: the enum of include/vbnn.h next to vbnn_ctx_create_ex
-M.STREAM_GIVEN, M.STREAM_LEGACY_DEFAULT = 0, 1
+M.STREAM_GIVEN, M.STREAM_LEGACY_DEFAULT, M.STREAM_PRIVATE_BLOCKING = 0, 1, 2
 
 -- cutorch's CURRENT stream, the one nn.ReLU / nn.LogSoftMax / the criterion (mlp.lua:19,27,30,32) enqueue on:
 -- THCState_getCurrentStream(cutorch.getState()) from libTHC.  cutorch's default stream -- and the only
@@ -83,14 +83,21 @@ local function cutorch_stream()
    return nil                                   -- stream 0 (or a cutorch without streams)
 end
 
--- one context per process, on cutorch's current device and stream
-function M.context(seed)
+-- one context per process, on cutorch's current device and stream.
+-- layer level (lua/VBLinear.lua; default): the library runs ON cutorch's stream -- stream 0 itself when that is the
+--   current one -- so every call is ordered with the neighbouring cunn modules like one of them;
+-- net level (lua/mlp.lua passes net_level = true): the whole minibatch is inside the library, which then wants CUDA graph
+--   replay; stream 0 cannot be captured, so it takes a private BLOCKING stream, which still synchronises implicitly with
+--   stream 0 (inputs:cuda() before, scalar reads after).
+function M.context(seed, net_level)
    if not M.ctx then
       local out = ffi.new('vbnn_ctx*[1]')
       local dev = cutorch.getDevice() - 1
       local stream = cutorch_stream()
       if stream ~= nil then
          M.check(C.vbnn_ctx_create_ex(dev, stream, M.STREAM_GIVEN, seed or 3, out))
+      elseif net_level then
+         M.check(C.vbnn_ctx_create_ex(dev, nil, M.STREAM_PRIVATE_BLOCKING, seed or 3, out))
       else
          M.check(C.vbnn_ctx_create_ex(dev, nil, M.STREAM_LEGACY_DEFAULT, seed or 3, out))
       end
