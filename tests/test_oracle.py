@@ -264,3 +264,32 @@ def test_sgd_matches_torch_optim():
         opt.step()
         O.optim_sgd(x, g, state)
     assert torch.allclose(x, p.detach(), atol=1e-15)
+
+
+def test_train_epoch_is_the_shuffled_sequence_of_minibatches():
+    """main:train (main.lua:13-53): the oracle's epoch loop visits the given start indices in order, assembles rows
+    [t, t + batchSize) (data.lua:9-20) and returns (accuracy / B, error / B) with B = trainSize / batchSize."""
+    import copy
+    opt = O.default_opt(input_size=12, hidden=[9], classes=list("abc"), S=2, B=6.0, batchSize=5, trainSize=20, mu_init=1,
+                        var_init=0.01)
+    net = O.MLPOracle(opt, torch.float64, seed=3)
+    ref = copy.deepcopy(net)
+    rng = np.random.RandomState(4)
+    ds = dict(inputs=torch.from_numpy(rng.randn(20, 12)), targets=torch.from_numpy(rng.randint(1, 4, 20).astype(np.float64)))
+    order = [10, 0, 15, 5]
+    eps = [[[torch.from_numpy(rng.randn(9, 12))] for _ in range(2)] for _ in order]
+    acc, err = O.train_epoch(net, ds, opt, order, eps_fn=lambda i: eps[i])
+    a = e = 0.0
+    for i, t in enumerate(order):
+        e_, a_ = O.train_minibatch(ref, ds["inputs"][t:t + 5], ds["targets"][t:t + 5], opt, eps=eps[i])
+        a += a_; e += e_
+    assert abs(acc - a / 4) < 1e-12 and abs(err - e / 4) < 1e-12
+    assert torch.equal(net.vb[0].means, ref.vb[0].means) and torch.equal(net.out.weight, ref.out.weight)
+
+
+def test_snr_prune_mask_restates_mainviz():
+    """mainviz.lua:20-22: pruned = lt(abs(means / sqrt(vars)), 0.005) with vars = exp(lvars)."""
+    means = torch.tensor([[0.0, 1e-4, 0.5], [-1e-5, 4.9e-4, -5.1e-4]], dtype=torch.float64)
+    lvars = torch.log(torch.tensor([[1e-2, 1e-2, 1e-2], [1e-6, 1e-2, 1e-2]], dtype=torch.float64))
+    mask, count = O.snr_prune_mask(means, lvars, 0.005)
+    assert mask.tolist() == [[True, True, False], [False, True, False]] and count == 3
