@@ -242,11 +242,12 @@ int pull_shards(vbnn_peer* P, const PeerBuf& b, int O, size_t row_bytes, int rpo
 // batch large: the stores need a fraction of NVLink).  With a small per-rank batch (strong scaling) the same bytes
 // must leave within a few microseconds per tile, the epilogue warps stall on posted remote stores and the tensor pipe
 // waits for its TMEM buffers (measured, C3 at 8 x 1024 rows: dW 196 TFLOP/s, 345 GB/s out of 900): there the tiles
-// are written to a LOCAL staging copy of the slot layout at full GEMM speed and the copy engines move one contiguous
-// slab per owner over NVLink while the SMs go on with the next GEMMs.
+// are written to a LOCAL staging copy of the slot layout at full GEMM speed and a small co-resident copy kernel (or,
+// knob 2, the copy engines) moves one contiguous slab per owner over NVLink while the GEMMs go on.
 bool peer_transport_ce(const vbnn_mlp* m, int N) {
   const int t = knobs().peer_transport;
   if (t == 1) return false;
+  if (!m->peer || m->peer->layers.empty() || !m->peer->layers[0].stage) return false;   // set up without a staging copy
   if (t == 2 || t == 3) return true;
   // Per layer and rank the dW GEMMs take t_dw ~ 4 * rows * O * I / 1.3e15 s while 8 * O * I * (G - 1) / G bytes must leave over
   // NVLink (t_link at ~700 GB/s): the fused stores hide while t_link < t_dw / 2, i.e. rows > 7428 * (G - 1) / G
