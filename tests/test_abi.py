@@ -99,3 +99,29 @@ def test_debug_knobs_and_ctx_create_ex_argument_checks():
     fake = C.c_void_p(0x10)
     assert lib.vbnn_ctx_create_ex(0, fake, _lib.STREAM_LEGACY_DEFAULT, 3, C.byref(h)) == _lib.E_INVALID   # stream must be NULL
     assert b"stream must be NULL" in lib.vbnn_last_error()
+
+
+def test_lua_shim_blocks_are_balanced():
+    """No Lua interpreter exists here: at least every function / if / for / while / do has its `end` and the brackets match
+    in the three shim files (a slip there would only surface on a user's machine)."""
+    for fn in ("vbnn_ffi.lua", "VBLinear.lua", "mlp.lua"):
+        src = open(os.path.join(ROOT, "lua", fn)).read()
+        src = re.sub(r"\[\[.*?\]\]", "", src, flags=re.S)
+        src = re.sub(r"--[^\n]*", "", src)
+        src = re.sub(r"'[^'\n]*'|\"[^\"\n]*\"", "''", src)
+        depth = pending_do = 0
+        for t in re.findall(r"\b(function|if|for|while|do|end)\b", src):
+            if t in ("function", "if"):
+                depth += 1
+            elif t in ("for", "while"):
+                depth += 1; pending_do += 1
+            elif t == "do":
+                if pending_do:
+                    pending_do -= 1
+                else:
+                    depth += 1
+            else:
+                depth -= 1
+            assert depth >= 0, fn
+        assert depth == 0, fn
+        assert src.count("(") == src.count(")") and src.count("{") == src.count("}"), fn
